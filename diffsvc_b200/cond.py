@@ -1,0 +1,55 @@
+"""Conditioning encoder used when the reference's `modules.fastspeech.fs2.FastSpeech2` is not
+importable (stand-alone tests / bench).  It restates, in PyTorch on whatever device the inputs are
+on, the `no_fs2` path of FastSpeech2.forward (modules/fastspeech/fs2.py:94-154, add_pitch :185-238,
+utils/pitch_utils.py:17-31,63-76).  One-off per utterance: SURVEY.md section 8(f) row 1 ("next").
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .hparams import hparams
+
+
+def f0_to_coarse(f0, hp):
+    f0_bin, f0_max, f0_min = hp["f0_bin"], hp["f0_max"], hp["f0_min"]
+    mel_min = 1127 * np.log(1 + f0_min / 700)
+    mel_max = 1127 * np.log(1 + f0_max / 700)
+    f0_mel = 1127 * (1 + f0 / 700).log()
+    f0_mel[f0_mel > 0] = (f0_mel[f0_mel > 0] - mel_min) * (f0_bin - 2) / (mel_max - mel_min) + 1
+    f0_mel[f0_mel <= 1] = 1
+    f0_mel[f0_mel > f0_bin - 1] = f0_bin - 1
+    return (f0_mel + 0.5).long()
+
+
+class CondEncoder(nn.Module):
+    """State-dict compatible with the reference for the one tensor this path reads: `pitch_embed.weight`."""
+
+    def __init__(self, dictionary=None, out_dims=None):
+        super().__init__()
+        self.hidden_size = hparams["hidden_size"]
+        self.padding_idx = 0
+        self.pitch_embed = nn.Embedding(300, self.hidden_size, self.padding_idx)
+        nn.init.normal_(self.pitch_embed.weight, mean=0, std=self.hidden_size ** -0.5)
+        nn.init.constant_(self.pitch_embed.weight[self.padding_idx], 0)
+
+    def forward(self, hubert, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None, energy=None,
+                skip_decoder=True, spk_embed_dur_id=None, spk_embed_f0_id=None, infer=False, **kwargs):
+        if not hparams.get("no_fs2", True) or hparams.get("use_spk_embed") or hparams.get("use_spk_id") \
+                or hparams.get("use_energy_embed") or hparams.get("pitch_norm", "log") != "log":
+            raise NotImplementedError("stand-alone CondEncoder covers the config_nsf.yaml conditioning only; "
+                                      "run inside the reference tree to use its FastSpeech2")
+        ret = {"mel2ph": mel2ph}
+        decoder_inp = F.pad(hubert, [0, 0, 1, 0])
+        mel2ph_ = mel2ph[..., None].repeat([1, 1, hubert.shape[-1]])
+        decoder_inp = torch.gather(decoder_inp, 1, mel2ph_)
+        tgt_nonpadding = (mel2ph > 0).float()[:, :, None]
+        pitch_padding = (mel2ph == 0)
+        f0_denorm = 2 ** f0
+        f0_denorm[pitch_padding] = 0
+        ret["f0_denorm"] = f0_denorm
+        f0[pitch_padding] = 0                                  # fs2.py:226-227 (in-place on the caller's tensor)
+        pitch = f0_to_coarse(f0_denorm, hparams)
+        ret["pitch_pred"] = pitch.unsqueeze(-1)
+        ret["decoder_inp"] = (decoder_inp + self.pitch_embed(pitch)) * tgt_nonpadding
+        return ret

@@ -1,0 +1,595 @@
+// DiffNet denoiser + DDPM / PLMS samplers: host orchestration, weight repacking, small kernels.
+// Reference: network/diff/net.py:58-135, network/diff/diffusion.py:146-198,269-278.
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "simt_gemm.cuh"
+#include "tc_gemm.cuh"
+
+#include <cmath>
+#include <memory>
+
+namespace dsvc {
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+
+// [B][R][Cc] (Cc contiguous) -> [B][Cc][R] tiled transpose, optional operand-plane copy of the output
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, Plane pl, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const float* ib = in + (size_t)b * R * Cc;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? ib[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) {
+      const float v = tile[threadIdx.x][i];
+      const size_t idx = ((size_t)b * Cc + c) * R + r;
+      if (out) out[idx] = v;
+      if (pl.f32) pl.f32[idx] = v;
+      if (pl.hi) {
+        __half h, l;
+        split_f16(v, h, l);
+        pl.hi[idx] = h;
+        pl.lo[idx] = l;
+      }
+    }
+  }
+}
+
+__global__ void set_state_kernel(StepState* st, int t, int interval) {
+  st->t = t;
+  st->t_prev = max(t - interval, 0);
+  st->interval = interval;
+  st->step = 0;
+  st->n_hist = 0;
+  st->head = 0;
+}
+
+// end-of-step bookkeeping: t -= interval, history ring advances (PLMS)
+__global__ void advance_state_kernel(StepState* st, int plms) {
+  const int dec = st->interval;
+  const int t = st->t - dec;
+  st->t = t;
+  st->t_prev = max(t - dec, 0);
+  st->step += 1;
+  if (plms) {
+    st->n_hist = min(st->n_hist + 1, 3);
+    st->head = (st->head + 1) & 3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct F16Pair {           // tcgen05 operand: fp16 hi/lo copies of a (power-of-two scaled) weight matrix
+  DevBuf hi, lo;
+  float inv_scale = 1.f;   // multiply the accumulator by this in the epilogue
+};
+
+struct PlaneBuf {
+  DevBuf f32, hi, lo;
+  Plane view(bool tc) const {
+    Plane p;
+    p.f32 = tc ? nullptr : f32.as<float>();
+    p.hi = tc ? hi.as<__half>() : nullptr;
+    p.lo = tc ? lo.as<__half>() : nullptr;
+    return p;
+  }
+  int reserve(size_t elems, bool tc) {
+    if (tc) {
+      DSVC_TRY(hi.reserve(elems * sizeof(__half)));
+      DSVC_TRY(lo.reserve(elems * sizeof(__half)));
+    } else {
+      DSVC_TRY(f32.reserve(elems * sizeof(float)));
+    }
+    return DSVC_OK;
+  }
+};
+
+}  // namespace dsvc
+
+using namespace dsvc;
+
+struct dsvc_diffnet {
+  dsvc_diffnet_config cfg;
+  bool tc = false;       // tcgen05 path
+  int passes = 3;
+  // fp32 weights (GEMM layouts: [taps][Cout][Cin])
+  DevBuf w_in, b_in, w_dil, w_cond, b_cond, w_out, b_out, w_skip, b_skip, w_head, b_head;
+  DevBuf dtab;           // [Tn][L][C]
+  // tcgen05 operands
+  F16Pair h_in, h_skip, h_head;
+  std::vector<std::unique_ptr<F16Pair>> h_dil, h_out;
+  // schedule
+  DevBuf c_recip, c_recipm1, c_coef1, c_coef2, c_logvar, c_acp;
+  bool have_schedule = false;
+  // workspace
+  int B = 0, Tmax = 0;
+  bool prepared = false;
+  DevBuf X, S, XS, hist, CP, cond_cl, lengths, state;
+  PlaneBuf Y, Z, SP, R, XIN;
+  TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
+  // CUDA graphs of one sampler step
+  cudaGraphExec_t g_ddpm = nullptr, g_plms = nullptr;
+  const float* g_ddpm_noise = nullptr;
+  unsigned long long g_ddpm_seed = 0;
+  bool g_ddpm_valid = false, g_plms_valid = false;
+
+  ~dsvc_diffnet() {
+    if (g_ddpm) cudaGraphExecDestroy(g_ddpm);
+    if (g_plms) cudaGraphExecDestroy(g_plms);
+  }
+};
+
+namespace dsvc {
+
+static int upload_f(DevBuf& b, const std::vector<float>& v, cudaStream_t s) {
+  return b.upload(v.data(), v.size() * sizeof(float), s);
+}
+
+// fp16 hi/lo split of a weight matrix with a power-of-two pre-scale that moves the weights into
+// fp16's normal range (hi + lo reproduces w * scale to ~2^-22).
+static int make_f16_pair(F16Pair& out, const float* w, size_t n, cudaStream_t s) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(w[i]));
+  float scale = 1.f;
+  if (mx > 0.f) {
+    int e;
+    std::frexp(1024.0f / mx, &e);          // 1024/mx = m * 2^e, m in [0.5,1)
+    scale = std::ldexp(1.0f, e - 1);        // largest power of two <= 1024/mx
+  }
+  std::vector<__half> hi(n), lo(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float v = w[i] * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+  out.inv_scale = 1.0f / scale;
+  DSVC_TRY(out.hi.upload(hi.data(), n * sizeof(__half), s));
+  DSVC_TRY(out.lo.upload(lo.data(), n * sizeof(__half), s));
+  DSVC_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+  return DSVC_OK;
+}
+
+static int gemm_affine(const float* A, const float* W, const float* bias, float* out, int rows, int Cin, int Cout,
+                       int act, cudaStream_t s) {
+  ConvGemmParams p{};
+  p.A = A; p.W = W; p.B = 1; p.Lin = rows; p.Cin = Cin; p.Cout = Cout; p.taps = 1; p.rows = rows;
+  p.in_stride = 1; p.in_off = 0; p.tap_step = 0; p.nphase = 1; p.tpad = 0; p.in_slope = 1.0f;
+  p.a_batch_stride = (long long)rows * Cin;
+  EpiAffine::Params e{};
+  e.bias = bias; e.res = nullptr; e.out = out; e.Lout = rows; e.Cout = Cout; e.accumulate = 0; e.div = 1.0f; e.act = act;
+  return launch_conv_gemm_tile<64, 128, 4, 8, EpiAffine>(p, e, s);
+}
+
+static int build(dsvc_diffnet* h, const dsvc_diffnet_weights* w, cudaStream_t s) {
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, H = h->cfg.encoder_hidden, L = h->cfg.residual_layers;
+  const int Tn = h->cfg.num_timesteps;
+  DSVC_TRY(h->w_in.upload(w->input_projection_w, (size_t)C * M * 4, s));
+  DSVC_TRY(h->b_in.upload(w->input_projection_b, (size_t)C * 4, s));
+  DSVC_TRY(h->w_skip.upload(w->skip_projection_w, (size_t)C * C * 4, s));
+  DSVC_TRY(h->b_skip.upload(w->skip_projection_b, (size_t)C * 4, s));
+  DSVC_TRY(h->w_head.upload(w->output_projection_w, (size_t)M * C * 4, s));
+  DSVC_TRY(h->b_head.upload(w->output_projection_b, (size_t)M * 4, s));
+
+  // dilated convs: [2C][C][3] -> [L][tap][2C paired][C]; pairing puts, in every 128-column tile,
+  // 64 gate rows next to their 64 filter rows so one CTA/thread owns both halves of the gate.
+  std::vector<float> wd((size_t)L * 3 * 2 * C * C), wc((size_t)L * 2 * C * H), bc((size_t)L * 2 * C),
+      wo((size_t)L * 2 * C * C), bo((size_t)L * 2 * C);
+  for (int l = 0; l < L; ++l) {
+    const float* src = w->dilated_conv_w[l];
+    for (int j = 0; j < 3; ++j)
+      for (int pn = 0; pn < 2 * C; ++pn) {
+        const int tile = pn / 128, within = pn % 128;
+        const int orig = within < 64 ? tile * 64 + within : C + tile * 64 + (within - 64);
+        float* dst = &wd[(((size_t)l * 3 + j) * 2 * C + pn) * C];
+        for (int ci = 0; ci < C; ++ci) dst[ci] = src[((size_t)orig * C + ci) * 3 + j];
+      }
+    memcpy(&wc[(size_t)l * 2 * C * H], w->conditioner_proj_w[l], (size_t)2 * C * H * 4);
+    for (int n = 0; n < 2 * C; ++n) bc[(size_t)l * 2 * C + n] = w->conditioner_proj_b[l][n] + w->dilated_conv_b[l][n];
+    memcpy(&wo[(size_t)l * 2 * C * C], w->output_proj_w[l], (size_t)2 * C * C * 4);
+    memcpy(&bo[(size_t)l * 2 * C], w->output_proj_b[l], (size_t)2 * C * 4);
+  }
+  DSVC_TRY(upload_f(h->w_cond, wc, s));
+  DSVC_TRY(upload_f(h->b_cond, bc, s));
+  DSVC_TRY(upload_f(h->b_out, bo, s));
+  if (!h->tc) {
+    DSVC_TRY(upload_f(h->w_dil, wd, s));
+    DSVC_TRY(upload_f(h->w_out, wo, s));
+  } else {
+    DSVC_TRY(make_f16_pair(h->h_in, w->input_projection_w, (size_t)C * M, s));
+    DSVC_TRY(make_f16_pair(h->h_skip, w->skip_projection_w, (size_t)C * C, s));
+    DSVC_TRY(make_f16_pair(h->h_head, w->output_projection_w, (size_t)M * C, s));
+    for (int l = 0; l < L; ++l) {
+      h->h_dil.emplace_back(new F16Pair());
+      h->h_out.emplace_back(new F16Pair());
+      DSVC_TRY(make_f16_pair(*h->h_dil[l], &wd[(size_t)l * 3 * 2 * C * C], (size_t)3 * 2 * C * C, s));
+      DSVC_TRY(make_f16_pair(*h->h_out[l], &wo[(size_t)l * 2 * C * C], (size_t)2 * C * C, s));
+    }
+  }
+
+  // step table D[t][l][:] = diffusion_projection_l(mlp(sinusoid(t)))  (net.py:124-125, :67)
+  DevBuf basis, w0, b0, w2, b2, wp, bp, t1, t2;
+  std::vector<float> wpv((size_t)L * C * C), bpv((size_t)L * C);
+  for (int l = 0; l < L; ++l) {
+    memcpy(&wpv[(size_t)l * C * C], w->diffusion_proj_w[l], (size_t)C * C * 4);
+    memcpy(&bpv[(size_t)l * C], w->diffusion_proj_b[l], (size_t)C * 4);
+  }
+  DSVC_TRY(basis.upload(w->step_basis, (size_t)Tn * C * 4, s));
+  DSVC_TRY(w0.upload(w->mlp0_w, (size_t)4 * C * C * 4, s));
+  DSVC_TRY(b0.upload(w->mlp0_b, (size_t)4 * C * 4, s));
+  DSVC_TRY(w2.upload(w->mlp2_w, (size_t)4 * C * C * 4, s));
+  DSVC_TRY(b2.upload(w->mlp2_b, (size_t)C * 4, s));
+  DSVC_TRY(upload_f(wp, wpv, s));
+  DSVC_TRY(upload_f(bp, bpv, s));
+  DSVC_TRY(t1.reserve((size_t)Tn * 4 * C * 4));
+  DSVC_TRY(t2.reserve((size_t)Tn * C * 4));
+  DSVC_TRY(h->dtab.reserve((size_t)Tn * L * C * 4));
+  DSVC_TRY(gemm_affine(basis.as<float>(), w0.as<float>(), b0.as<float>(), t1.as<float>(), Tn, C, 4 * C, EpiAffine::ACT_MISH, s));
+  DSVC_TRY(gemm_affine(t1.as<float>(), w2.as<float>(), b2.as<float>(), t2.as<float>(), Tn, 4 * C, C, EpiAffine::ACT_NONE, s));
+  DSVC_TRY(gemm_affine(t2.as<float>(), wp.as<float>(), bp.as<float>(), h->dtab.as<float>(), Tn, C, L * C, EpiAffine::ACT_NONE, s));
+  DSVC_CUDA(cudaStreamSynchronize(s));   // temporaries are freed on return
+  return DSVC_OK;
+}
+
+// TMA descriptors of every contraction of the tcgen05 path (depend on B, Tmax and the workspace)
+static int tc_build_maps(dsvc_diffnet* h) {
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
+  const int B = h->B, T = h->Tmax;
+  auto gemm = [&](TcGemmMaps& g, const PlaneBuf& a, int K, const F16Pair& w, int rows) -> int {
+    DSVC_TRY(tc_make_a_map(&g.a_hi, a.hi.as<__half>(), B, T, K));
+    DSVC_TRY(tc_make_a_map(&g.a_lo, a.lo.as<__half>(), B, T, K));
+    DSVC_TRY(tc_make_b_map(&g.b_hi, w.hi.as<__half>(), rows, K));
+    DSVC_TRY(tc_make_b_map(&g.b_lo, w.lo.as<__half>(), rows, K));
+    return DSVC_OK;
+  };
+  DSVC_TRY(gemm(h->maps.in, h->XIN, M, h->h_in, C));
+  DSVC_TRY(gemm(h->maps.skip, h->SP, C, h->h_skip, C));
+  DSVC_TRY(gemm(h->maps.head, h->R, C, h->h_head, M));
+  h->maps.dil.resize(L);
+  h->maps.out.resize(L);
+  for (int l = 0; l < L; ++l) {
+    DSVC_TRY(gemm(h->maps.dil[l], h->Y, C, *h->h_dil[l], 3 * 2 * C));
+    DSVC_TRY(gemm(h->maps.out[l], h->Z, C, *h->h_out[l], 2 * C));
+  }
+  return DSVC_OK;
+}
+
+// ---- one denoiser evaluation: enqueue all kernels on `s` --------------------------------------
+struct HeadArgs {
+  int mode = HEAD_EVAL;
+  float* out = nullptr;
+  const float* noise = nullptr;
+  unsigned long long seed = 0;
+  int tsel = 0;   // 0: step table row st->t, 1: st->t_prev (second eval of the first PLMS iteration)
+};
+
+static ConvGemmParams base_params(const float* A, const float* W, int B, int T, int Cin, int Cout, int taps, int dil) {
+  ConvGemmParams p{};
+  p.A = A; p.W = W; p.B = B; p.Lin = T; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.rows = T;
+  p.in_stride = 1; p.in_off = (taps == 3) ? -dil : 0; p.tap_step = dil; p.nphase = 1; p.tpad = 0; p.in_slope = 1.0f;
+  p.a_batch_stride = (long long)T * Cin;
+  return p;
+}
+
+template <class Epi>
+static int launch_fp32(const dsvc_diffnet* h, const ConvGemmParams& p, const typename Epi::Params& e, cudaStream_t s) {
+  // 64-row tiles when the 128-row grid would leave most of the 148 SMs idle
+  const long long ctas128 = (long long)ceil_div(p.rows, 128) * ceil_div(p.Cout, 128) * p.B;
+  if (ctas128 >= 2 * 148) return launch_conv_gemm_tile<128, 128, 8, 8, Epi>(p, e, s);
+  return launch_conv_gemm_tile<64, 128, 4, 8, Epi>(p, e, s);
+}
+
+// K3a: dilated conv + hoisted conditioner + gate -> Z
+static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
+  const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
+  const bool tc = h->tc;
+  const int dil = 1 << (l % h->cfg.dilation_cycle_length);
+  EpiGate::Params e{};
+  e.CP = h->CP.as<float>() + (size_t)l * B * T * 2 * C; e.Z = h->Z.view(tc); e.Tmax = T; e.C = C;
+  if (tc) {
+    e.wscale = h->h_dil[l]->inv_scale;
+    return tc_launch<EpiGate>(h->maps.dil[l], e, B, T, C, 2 * C, 3, dil, h->passes, s);
+  }
+  e.wscale = 1.f;
+  const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;
+  return launch_fp32<EpiGate>(h, base_params(h->Y.f32.as<float>(), W, B, T, C, 2 * C, 3, dil), e, s);
+}
+
+// K3b: output projection + residual + skip
+static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
+  const int C = h->cfg.residual_channels, L = h->cfg.residual_layers, B = h->B, T = h->Tmax;
+  const bool tc = h->tc;
+  EpiOutProj::Params e{};
+  e.bias = h->b_out.as<float>() + (size_t)l * 2 * C; e.dtab = h->dtab.as<float>(); e.st = h->state.as<StepState>();
+  e.lengths = h->lengths.as<int>();
+  e.X = h->X.as<float>(); e.S = h->S.as<float>(); e.Y = h->Y.view(tc); e.SP = h->SP.view(tc);
+  e.Tmax = T; e.C = C; e.L = L; e.layer = l; e.tsel = tsel;
+  if (tc) {
+    e.wscale = h->h_out[l]->inv_scale;
+    return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s);
+  }
+  e.wscale = 1.f;
+  const float* W = h->w_out.as<float>() + (size_t)l * 2 * C * C;
+  return launch_fp32<EpiOutProj>(h, base_params(h->Z.f32.as<float>(), W, B, T, C, 2 * C, 1, 0), e, s);
+}
+
+static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
+  const int B = h->B, T = h->Tmax;
+  const bool tc = h->tc;
+  const StepState* st = h->state.as<StepState>();
+  const int* len = h->lengths.as<int>();
+  const float* dtab = h->dtab.as<float>();
+
+  // K0 input_projection + ReLU
+  {
+    EpiInProj::Params e{};
+    e.bias = h->b_in.as<float>(); e.dtab = dtab; e.st = st; e.lengths = len; e.X = h->X.as<float>();
+    e.Y = h->Y.view(tc); e.Tmax = T; e.C = C; e.L = L; e.tsel = ha.tsel;
+    if (tc) {
+      e.wscale = h->h_in.inv_scale;
+      DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s));
+    } else {
+      e.wscale = 1.f;
+      DSVC_TRY(launch_fp32<EpiInProj>(h, base_params(h->XIN.f32.as<float>(), h->w_in.as<float>(), B, T, M, C, 1, 0), e, s));
+    }
+  }
+  for (int l = 0; l < L; ++l) {
+    DSVC_TRY(enqueue_layer_conv(h, l, s));
+    DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s));
+  }
+  {  // K4a skip_projection + ReLU
+    EpiSkipProj::Params e{};
+    e.bias = h->b_skip.as<float>(); e.R = h->R.view(tc); e.Tmax = T; e.C = C;
+    if (tc) {
+      e.wscale = h->h_skip.inv_scale;
+      DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s));
+    } else {
+      e.wscale = 1.f;
+      DSVC_TRY(launch_fp32<EpiSkipProj>(h, base_params(h->SP.f32.as<float>(), h->w_skip.as<float>(), B, T, C, C, 1, 0), e, s));
+    }
+  }
+  {  // K4b output_projection + sampler update
+    EpiHead::Params e{};
+    e.bias = h->b_head.as<float>(); e.st = st; e.mode = ha.mode; e.B = B; e.Tmax = T; e.M = M;
+    e.out = ha.out; e.xs = h->XS.as<float>(); e.XIN = h->XIN.view(tc);
+    e.c_recip = h->c_recip.as<float>(); e.c_recipm1 = h->c_recipm1.as<float>(); e.c_coef1 = h->c_coef1.as<float>();
+    e.c_coef2 = h->c_coef2.as<float>(); e.c_logvar = h->c_logvar.as<float>(); e.noise = ha.noise; e.seed = ha.seed;
+    e.alphas_cumprod = h->c_acp.as<float>(); e.hist = h->hist.as<float>();
+    if (tc) {
+      e.wscale = h->h_head.inv_scale;
+      DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s));
+    } else {
+      e.wscale = 1.f;
+      DSVC_TRY(launch_fp32<EpiHead>(h, base_params(h->R.f32.as<float>(), h->w_head.as<float>(), B, T, C, M, 1, 0), e, s));
+    }
+  }
+  return DSVC_OK;
+}
+
+static int load_x(dsvc_diffnet* h, const float* spec, cudaStream_t s) {
+  // [B][M][T] -> XS [B][T][M] (+ operand plane of input_projection)
+  const int M = h->cfg.mel_bins;
+  dim3 grid(ceil_div(h->Tmax, 32), ceil_div(M, 32), h->B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(spec, h->XS.as<float>(), h->XIN.view(h->tc), M, h->Tmax);
+  DSVC_LAUNCH_CHECK();
+  return DSVC_OK;
+}
+
+static int store_x(dsvc_diffnet* h, float* x, cudaStream_t s) {
+  const int M = h->cfg.mel_bins;
+  Plane none{nullptr, nullptr, nullptr};
+  dim3 grid(ceil_div(M, 32), ceil_div(h->Tmax, 32), h->B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(h->XS.as<float>(), x, none, h->Tmax, M);
+  DSVC_LAUNCH_CHECK();
+  return DSVC_OK;
+}
+
+// capture `body` (which enqueues on s) into an executable graph
+template <class F>
+static int capture_graph(cudaGraphExec_t* exec, cudaStream_t s, F body) {
+  if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+  cudaGraph_t g = nullptr;
+  DSVC_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int r = body();
+  cudaError_t ce = cudaStreamEndCapture(s, &g);
+  if (r != DSVC_OK) { if (g) cudaGraphDestroy(g); return r; }
+  DSVC_CUDA(ce);
+  ce = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  DSVC_CUDA(ce);
+  return DSVC_OK;
+}
+
+}  // namespace dsvc
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int dsvc_diffnet_create(dsvc_diffnet_t** out, const dsvc_diffnet_config* cfg, const dsvc_diffnet_weights* w, void* stream) {
+  DSVC_REQUIRE(out && cfg && w, "dsvc_diffnet_create: null argument");
+  DSVC_TRY(require_device());
+  const int M = cfg->mel_bins, C = cfg->residual_channels, H = cfg->encoder_hidden, L = cfg->residual_layers;
+  DSVC_REQUIRE(M > 0 && C > 0 && H > 0 && L > 0 && cfg->num_timesteps > 0 && cfg->dilation_cycle_length > 0,
+               "dsvc_diffnet_create: non-positive dimension");
+  DSVC_REQUIRE(C % 64 == 0, "residual_channels must be a multiple of 64 (got %d)", C);
+  DSVC_REQUIRE(M % 4 == 0 && H % 4 == 0, "mel_bins and encoder_hidden must be multiples of 4");
+  DSVC_REQUIRE(cfg->math == DSVC_MATH_TC3F16 || cfg->math == DSVC_MATH_FP32 || cfg->math == DSVC_MATH_TC1F16,
+               "unknown math mode %d", cfg->math);
+  if (cfg->math != DSVC_MATH_FP32)
+    DSVC_REQUIRE(M % 64 == 0 && C % 128 == 0, "tensor-core math needs mel_bins %% 64 == 0 and residual_channels %% 128 == 0 "
+                 "(got M=%d C=%d); use DSVC_MATH_FP32", M, C);
+  dsvc_diffnet* h = new dsvc_diffnet();
+  h->cfg = *cfg;
+  h->tc = cfg->math != DSVC_MATH_FP32;
+  h->passes = cfg->math == DSVC_MATH_TC1F16 ? 1 : 3;
+  int r = build(h, w, (cudaStream_t)stream);
+  if (r != DSVC_OK) { delete h; return r; }
+  *out = h;
+  return DSVC_OK;
+}
+
+void dsvc_diffnet_destroy(dsvc_diffnet_t* h) { delete h; }
+
+int dsvc_diffnet_set_schedule(dsvc_diffnet_t* h, const float* recip, const float* recipm1, const float* coef1,
+                              const float* coef2, const float* logvar, const float* acp) {
+  DSVC_REQUIRE(h && recip && recipm1 && coef1 && coef2 && logvar && acp, "dsvc_diffnet_set_schedule: null argument");
+  const size_t n = (size_t)h->cfg.num_timesteps * 4;
+  DSVC_TRY(h->c_recip.upload(recip, n, 0));
+  DSVC_TRY(h->c_recipm1.upload(recipm1, n, 0));
+  DSVC_TRY(h->c_coef1.upload(coef1, n, 0));
+  DSVC_TRY(h->c_coef2.upload(coef2, n, 0));
+  DSVC_TRY(h->c_logvar.upload(logvar, n, 0));
+  DSVC_TRY(h->c_acp.upload(acp, n, 0));
+  DSVC_CUDA(cudaStreamSynchronize(0));
+  h->have_schedule = true;
+  return DSVC_OK;
+}
+
+int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32_t* lengths, const float* cond, void* stream) {
+  DSVC_REQUIRE(h && cond, "dsvc_diffnet_prepare: null argument");
+  DSVC_REQUIRE(B > 0 && Tmax > 0, "dsvc_diffnet_prepare: B and Tmax must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, H = h->cfg.encoder_hidden, L = h->cfg.residual_layers;
+  const bool tc = h->tc;
+  std::vector<int> len(B, Tmax);
+  if (lengths)
+    for (int b = 0; b < B; ++b) {
+      DSVC_REQUIRE(lengths[b] >= 0 && lengths[b] <= Tmax, "lengths[%d]=%d outside [0,%d]", b, lengths[b], Tmax);
+      len[b] = lengths[b];
+    }
+  const bool resized = (B != h->B || Tmax != h->Tmax);
+  h->B = B; h->Tmax = Tmax;
+  const size_t n = (size_t)B * Tmax;
+  DSVC_TRY(h->X.reserve(n * C * 4));
+  DSVC_TRY(h->S.reserve(n * C * 4));
+  DSVC_TRY(h->XS.reserve(n * M * 4));
+  DSVC_TRY(h->hist.reserve(4 * n * M * 4));
+  DSVC_TRY(h->CP.reserve((size_t)L * n * 2 * C * 4));
+  DSVC_TRY(h->cond_cl.reserve(n * H * 4));
+  DSVC_TRY(h->lengths.reserve((size_t)B * 4));
+  DSVC_TRY(h->state.reserve(sizeof(StepState)));
+  DSVC_TRY(h->Y.reserve(n * C, tc));
+  DSVC_TRY(h->Z.reserve(n * C, tc));
+  DSVC_TRY(h->SP.reserve(n * C, tc));
+  DSVC_TRY(h->R.reserve(n * C, tc));
+  DSVC_TRY(h->XIN.reserve(n * M, tc));
+  DSVC_CUDA(cudaMemcpyAsync(h->lengths.p, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  DSVC_CUDA(cudaStreamSynchronize(s));   // `len` is a stack-owned staging buffer
+  if (resized || !h->prepared) {
+    h->g_ddpm_valid = h->g_plms_valid = false;
+    if (tc) DSVC_TRY(tc_build_maps(h));
+  }
+  // cond [B][H][T] -> channels-last, then all L conditioner projections in one GEMM
+  {
+    Plane none{nullptr, nullptr, nullptr};
+    dim3 grid(ceil_div(Tmax, 32), ceil_div(H, 32), B), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(cond, h->cond_cl.as<float>(), none, H, Tmax);
+    DSVC_LAUNCH_CHECK();
+    ConvGemmParams p = base_params(h->cond_cl.as<float>(), h->w_cond.as<float>(), B, Tmax, H, L * 2 * C, 1, 0);
+    EpiCondProj::Params e{};
+    e.bias = h->b_cond.as<float>(); e.CP = h->CP.as<float>(); e.B = B; e.Tmax = Tmax; e.C2 = 2 * C;
+    DSVC_TRY((launch_conv_gemm_tile<128, 128, 8, 8, EpiCondProj>(p, e, s)));
+  }
+  h->prepared = true;
+  return DSVC_OK;
+}
+
+int dsvc_diffnet_eval(dsvc_diffnet_t* h, const float* spec, int32_t t, float* out, void* stream) {
+  DSVC_REQUIRE(h && spec && out, "dsvc_diffnet_eval: null argument");
+  if (!h->prepared) { set_error("dsvc_diffnet_eval: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
+  DSVC_REQUIRE(t >= 0 && t < h->cfg.num_timesteps, "diffusion step %d outside [0,%d)", t, h->cfg.num_timesteps);
+  cudaStream_t s = (cudaStream_t)stream;
+  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t, 0);
+  DSVC_LAUNCH_CHECK();
+  DSVC_TRY(load_x(h, spec, s));
+  HeadArgs ha; ha.mode = HEAD_EVAL; ha.out = out;
+  return enqueue_eval(h, ha, s);
+}
+
+int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream) {
+  DSVC_REQUIRE(h, "dsvc_diffnet_run_layer: null handle");
+  if (!h->prepared) { set_error("dsvc_diffnet_run_layer: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
+  DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && (part == 0 || part == 1) && iters >= 0, "bad layer/part/iters");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < iters; ++i) {
+    if (part == 0) DSVC_TRY(enqueue_layer_conv(h, layer, s));
+    else DSVC_TRY(enqueue_layer_out(h, layer, 0, s));
+  }
+  return DSVC_OK;
+}
+
+int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* noise, uint64_t seed, void* stream) {
+  DSVC_REQUIRE(h && x, "dsvc_sample_ddpm: null argument");
+  if (!h->prepared || !h->have_schedule) { set_error("dsvc_sample_ddpm: prepare + set_schedule first"); return DSVC_ESTATE; }
+  DSVC_REQUIRE(t_start >= 0 && t_start <= h->cfg.num_timesteps, "t_start %d outside [0,%d]", t_start, h->cfg.num_timesteps);
+  cudaStream_t s = (cudaStream_t)stream;
+  DSVC_TRY(load_x(h, x, s));
+  if (t_start > 0) {
+    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t_start - 1, 1);
+    DSVC_LAUNCH_CHECK();
+    if (!h->g_ddpm_valid || h->g_ddpm_noise != noise || h->g_ddpm_seed != seed) {
+      HeadArgs ha; ha.mode = HEAD_DDPM; ha.noise = noise; ha.seed = seed;
+      DSVC_TRY(capture_graph(&h->g_ddpm, s, [&]() -> int {
+        DSVC_TRY(enqueue_eval(h, ha, s));
+        advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0);
+        DSVC_LAUNCH_CHECK();
+        return DSVC_OK;
+      }));
+      h->g_ddpm_valid = true; h->g_ddpm_noise = noise; h->g_ddpm_seed = seed;
+    }
+    const uint64_t per_step = 2ull * h->cfg.residual_layers + 4;
+    for (int i = 0; i < t_start; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm, s));
+    g_launches.fetch_add(per_step * (uint64_t)t_start, std::memory_order_relaxed);
+  }
+  return store_x(h, x, s);
+}
+
+int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t interval, void* stream) {
+  DSVC_REQUIRE(h && x, "dsvc_sample_plms: null argument");
+  if (!h->prepared || !h->have_schedule) { set_error("dsvc_sample_plms: prepare + set_schedule first"); return DSVC_ESTATE; }
+  DSVC_REQUIRE(interval >= 1, "interval must be >= 1");
+  DSVC_REQUIRE(t_start >= 0 && t_start <= h->cfg.num_timesteps, "t_start %d outside [0,%d]", t_start, h->cfg.num_timesteps);
+  cudaStream_t s = (cudaStream_t)stream;
+  DSVC_TRY(load_x(h, x, s));
+  // reversed(range(0, t_start, interval)): first t is the largest multiple of interval below t_start
+  const int n_iter = t_start > 0 ? (t_start - 1) / interval + 1 : 0;
+  if (n_iter > 0) {
+    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), (n_iter - 1) * interval, interval);
+    DSVC_LAUNCH_CHECK();
+    // first iteration: two evaluations (diffusion.py:184-187)
+    HeadArgs a; a.mode = HEAD_PLMS_FIRST; a.tsel = 0;
+    DSVC_TRY(enqueue_eval(h, a, s));
+    HeadArgs b2; b2.mode = HEAD_PLMS_SECOND; b2.tsel = 1;
+    DSVC_TRY(enqueue_eval(h, b2, s));
+    advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 1);
+    DSVC_LAUNCH_CHECK();
+    if (n_iter > 1) {
+      if (!h->g_plms_valid) {
+        HeadArgs c; c.mode = HEAD_PLMS_NEXT;
+        DSVC_TRY(capture_graph(&h->g_plms, s, [&]() -> int {
+          DSVC_TRY(enqueue_eval(h, c, s));
+          advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 1);
+          DSVC_LAUNCH_CHECK();
+          return DSVC_OK;
+        }));
+        h->g_plms_valid = true;
+      }
+      for (int i = 1; i < n_iter; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_plms, s));
+      g_launches.fetch_add((2ull * h->cfg.residual_layers + 4) * (uint64_t)(n_iter - 1), std::memory_order_relaxed);
+    }
+  }
+  return store_x(h, x, s);
+}
+
+}  // extern "C"

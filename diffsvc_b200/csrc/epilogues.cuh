@@ -1,0 +1,349 @@
+// Epilogue functors shared by the fp32 FFMA main loop (simt_gemm.cuh) and the tcgen05 main loop
+// (tc_gemm.cuh).  An epilogue sees one output row (b, op) and a chunk of 4 consecutive output
+// channels n..n+3 with their fp32 accumulators.
+//
+// Everything the WaveNet layer does besides its two contractions is fused here
+// (reference network/diff/net.py:66-84, :112-135 and network/diff/diffusion.py:146-198).
+#pragma once
+#include "common.cuh"
+
+namespace dsvc {
+
+// Device-resident sampler state, advanced by a 1-thread kernel at the end of each step so that one
+// captured CUDA graph serves every step of the loop.
+struct StepState {
+  int t;        // current diffusion step
+  int t_prev;   // PLMS: max(t - interval, 0)
+  int interval; // t decrement per step (1 for DDPM)
+  int step;     // number of completed steps (index of the noise slab to consume)
+  int n_hist;   // PLMS: valid entries in the eps history (0..3)
+  int head;     // PLMS: slot the current eps is written to (ring of 4)
+};
+
+// An operand "plane": the activation tensor a later contraction reads.  fp32 for the FFMA path;
+// an fp16 (hi, lo) pair, hi + lo == x to ~2^-22, for the 3-pass tcgen05 path.
+struct Plane {
+  float* f32;
+  __half* hi;
+  __half* lo;
+};
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__device__ __forceinline__ void plane_store4(const Plane& pl, size_t idx, const float (&v)[4]) {
+  if (pl.f32) *reinterpret_cast<float4*>(pl.f32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  if (pl.hi) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_f16(v[i], h[i], l[i]);
+    *reinterpret_cast<uint2*>(pl.hi + idx) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(pl.lo + idx) = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// ---- input_projection + ReLU (net.py:121,123), and the conv-input plane of layer 0 ----------
+struct EpiInProj {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;       // [C]
+    const float* dtab;       // [Tn][L][C] diffusion-step shifts d_l(t)
+    const StepState* st;
+    const int* lengths;      // [B]
+    float* X;                // [B][Tmax][C] residual stream
+    Plane Y;                 // (x + d_0) masked to the item's own length: what the dilated conv reads
+    int Tmax, C, L;
+    int tsel;                // 0: step-table row st->t; 1: st->t_prev (2nd eval of the first PLMS iteration)
+    float wscale;            // inverse power-of-two weight scale of the tcgen05 path (1 for FFMA)
+  };
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const int tt = e.tsel ? e.st->t_prev : e.st->t;
+    const float4 d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + 0) * e.C + n));
+    float x[4] = {fmaxf(a[0] * e.wscale + bi.x, 0.f), fmaxf(a[1] * e.wscale + bi.y, 0.f),
+                  fmaxf(a[2] * e.wscale + bi.z, 0.f), fmaxf(a[3] * e.wscale + bi.w, 0.f)};
+    const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
+    *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
+    const bool live = p < e.lengths[b];
+    float y[4] = {live ? x[0] + d.x : 0.f, live ? x[1] + d.y : 0.f, live ? x[2] + d.z : 0.f, live ? x[3] + d.w : 0.f};
+    plane_store4(e.Y, idx, y);
+  }
+};
+
+// ---- hoisted conditioner projections of all layers (net.py:68), + both conv biases ----------
+struct EpiCondProj {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;   // [L*2C]: conditioner_projection.bias + dilated_conv.bias
+    float* CP;           // [L][B][Tmax][2C]
+    int B, Tmax, C2;
+  };
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+    const int l = n / e.C2, nn = n - l * e.C2;
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const size_t idx = (((size_t)l * e.B + b) * e.Tmax + p) * e.C2 + nn;
+    *reinterpret_cast<float4*>(e.CP + idx) = make_float4(a[0] + bi.x, a[1] + bi.y, a[2] + bi.z, a[3] + bi.w);
+  }
+};
+
+// ---- gated activation: sigmoid(gate) * tanh(filter) (net.py:71-77) ---------------------------
+struct EpiGate {
+  static constexpr bool kPair = true;
+  struct Params {
+    const float* CP;     // this layer's slab [B][Tmax][2C] (biases folded in)
+    Plane Z;             // [B][Tmax][C]
+    int Tmax, C;
+    float wscale;
+  };
+  __device__ static __forceinline__ void apply_pair(const Params& e, int b, int p, int c0,
+                                                    const float (&g)[4], const float (&f)[4]) {
+    const size_t row = (size_t)b * e.Tmax + p;
+    const float4 cg = __ldg(reinterpret_cast<const float4*>(e.CP + row * (2 * e.C) + c0));
+    const float4 cf = __ldg(reinterpret_cast<const float4*>(e.CP + row * (2 * e.C) + e.C + c0));
+    const float gg[4] = {g[0] * e.wscale + cg.x, g[1] * e.wscale + cg.y, g[2] * e.wscale + cg.z, g[3] * e.wscale + cg.w};
+    const float ff[4] = {f[0] * e.wscale + cf.x, f[1] * e.wscale + cf.y, f[2] * e.wscale + cf.z, f[3] * e.wscale + cf.w};
+    float z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = sigmoidf_(gg[i]) * tanhf(ff[i]);
+    plane_store4(e.Z, row * e.C + c0, z);
+  }
+};
+
+// ---- output_projection: residual half -> x' = (x + r)/sqrt(2) (net.py:79-84); skip half -> running
+//      skip sum (net.py:129-131, never materialising the [L,B,C,T] stack) ----------------------
+struct EpiOutProj {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;       // [2C]
+    const float* dtab;       // [Tn][L][C]
+    const StepState* st;
+    const int* lengths;
+    float* X;                // [B][Tmax][C] in/out
+    float* S;                // [B][Tmax][C] running skip sum
+    Plane Y;                 // (x' + d_{l+1}) masked (not written by the last layer)
+    Plane SP;                // last layer only: sum(skip)/sqrt(L), operand of skip_projection
+    int Tmax, C, L, layer;
+    int tsel;
+    float wscale;
+  };
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const float v[4] = {a[0] * e.wscale + bi.x, a[1] * e.wscale + bi.y, a[2] * e.wscale + bi.z, a[3] * e.wscale + bi.w};
+    if (n < e.C) {
+      const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
+      const float4 xo = *reinterpret_cast<const float4*>(e.X + idx);
+      const float s2 = 1.41421356237309504880f;
+      float x[4] = {div_rn(add_rn(xo.x, v[0]), s2), div_rn(add_rn(xo.y, v[1]), s2),
+                    div_rn(add_rn(xo.z, v[2]), s2), div_rn(add_rn(xo.w, v[3]), s2)};
+      *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
+      if (e.layer + 1 < e.L) {
+        const int tt = e.tsel ? e.st->t_prev : e.st->t;
+        const float4 d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + e.layer + 1) * e.C + n));
+        const bool live = p < e.lengths[b];
+        float y[4] = {live ? x[0] + d.x : 0.f, live ? x[1] + d.y : 0.f, live ? x[2] + d.z : 0.f, live ? x[3] + d.w : 0.f};
+        plane_store4(e.Y, idx, y);
+      }
+    } else {
+      const size_t idx = ((size_t)b * e.Tmax + p) * e.C + (n - e.C);
+      float s[4] = {v[0], v[1], v[2], v[3]};
+      if (e.layer > 0) {
+        const float4 so = *reinterpret_cast<const float4*>(e.S + idx);
+        s[0] = add_rn(so.x, v[0]); s[1] = add_rn(so.y, v[1]); s[2] = add_rn(so.z, v[2]); s[3] = add_rn(so.w, v[3]);
+      }
+      if (e.layer + 1 < e.L) {
+        *reinterpret_cast<float4*>(e.S + idx) = make_float4(s[0], s[1], s[2], s[3]);
+      } else {
+        const float sl = sqrtf((float)e.L);
+        float q[4] = {div_rn(s[0], sl), div_rn(s[1], sl), div_rn(s[2], sl), div_rn(s[3], sl)};
+        plane_store4(e.SP, idx, q);
+      }
+    }
+  }
+};
+
+// ---- skip_projection + ReLU (net.py:132-133) -------------------------------------------------
+struct EpiSkipProj {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;   // [C]
+    Plane R;             // [B][Tmax][C]
+    int Tmax, C;
+    float wscale;
+  };
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    float r[4] = {fmaxf(a[0] * e.wscale + bi.x, 0.f), fmaxf(a[1] * e.wscale + bi.y, 0.f),
+                  fmaxf(a[2] * e.wscale + bi.z, 0.f), fmaxf(a[3] * e.wscale + bi.w, 0.f)};
+    plane_store4(e.R, ((size_t)b * e.Tmax + p) * e.C + n, r);
+  }
+};
+
+// ---- output_projection of DiffNet (net.py:134) fused with the sampler update ------------------
+enum HeadMode : int {
+  HEAD_EVAL = 0,        // write eps to `out` in the reference layout [B,1,M,T]
+  HEAD_DDPM = 1,        // p_sample (diffusion.py:146-163)
+  HEAD_PLMS_FIRST = 2,  // first eval of the first PLMS iteration: x_pred into the operand plane
+  HEAD_PLMS_SECOND = 3, // second eval: eps' -> (eps+eps')/2 -> x
+  HEAD_PLMS_NEXT = 4,   // Adams-Bashforth combination of the history (diffusion.py:188-196)
+};
+
+struct EpiHead {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;   // [M]
+    const StepState* st;
+    int mode;
+    int B, Tmax, M;
+    float wscale;
+    float* out;          // HEAD_EVAL: [B,1,M,Tmax]
+    float* xs;           // sampler state x, channels-last [B][Tmax][M]
+    Plane XIN;           // operand plane of input_projection for the next eval
+    // DDPM
+    const float* c_recip; const float* c_recipm1; const float* c_coef1; const float* c_coef2; const float* c_logvar;
+    const float* noise;  // [steps][B][1][M][Tmax] or null
+    unsigned long long seed;
+    // PLMS
+    const float* alphas_cumprod;
+    float* hist;         // [4][B][Tmax][M] eps ring
+  };
+
+  // get_x_pred coefficients (diffusion.py:171-177), evaluated in the reference's op order
+  __device__ static __forceinline__ void plms_coefs(const Params& e, float& dA, float& cx, float& ce) {
+    const float a_t = e.alphas_cumprod[e.st->t], a_prev = e.alphas_cumprod[e.st->t_prev];
+    const float a_t_sq = sqrtf(a_t), a_prev_sq = sqrtf(a_prev);
+    dA = sub_rn(a_prev, a_t);
+    cx = div_rn(1.0f, mul_rn(a_t_sq, add_rn(a_t_sq, a_prev_sq)));
+    const float s1 = sqrtf(mul_rn(sub_rn(1.0f, a_prev), a_t));
+    const float s2 = sqrtf(mul_rn(sub_rn(1.0f, a_t), a_prev));
+    ce = div_rn(1.0f, mul_rn(a_t_sq, add_rn(s1, s2)));
+  }
+  __device__ static __forceinline__ float x_pred(float x, float eps, float dA, float cx, float ce) {
+    return add_rn(x, mul_rn(dA, sub_rn(mul_rn(cx, x), mul_rn(ce, eps))));
+  }
+
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const float eps[4] = {a[0] * e.wscale + bi.x, a[1] * e.wscale + bi.y, a[2] * e.wscale + bi.z, a[3] * e.wscale + bi.w};
+    const size_t idx = ((size_t)b * e.Tmax + p) * e.M + n;
+    if (e.mode == HEAD_EVAL) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e.out[((size_t)b * e.M + n + i) * e.Tmax + p] = eps[i];
+      return;
+    }
+    const float4 xo = *reinterpret_cast<const float4*>(e.xs + idx);
+    const float x[4] = {xo.x, xo.y, xo.z, xo.w};
+    float xn[4];
+    if (e.mode == HEAD_DDPM) {
+      const int t = e.st->t;
+      const float cr = e.c_recip[t], crm1 = e.c_recipm1[t], c1 = e.c_coef1[t], c2 = e.c_coef2[t];
+      const float sd = (t == 0) ? 0.0f : expf(mul_rn(0.5f, e.c_logvar[t]));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x0 = sub_rn(mul_rn(cr, x[i]), mul_rn(crm1, eps[i]));       // predict_start_from_noise
+        x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                               // clamp_ (clip_denoised)
+        const float mean = add_rn(mul_rn(c1, x0), mul_rn(c2, x[i]));      // q_posterior
+        float nz;
+        const size_t nidx = (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p;
+        if (e.noise) nz = __ldg(e.noise + nidx);
+        else nz = philox_normal(e.seed, 0x6e6f6973u, nidx);
+        xn[i] = add_rn(mean, mul_rn(sd, nz));
+      }
+      *reinterpret_cast<float4*>(e.xs + idx) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      plane_store4(e.XIN, idx, xn);
+      return;
+    }
+    // ---- PLMS ----
+    const size_t hs = (size_t)e.B * e.Tmax * e.M;
+    float dA, cx, ce;
+    plms_coefs(e, dA, cx, ce);
+    const int head = e.st->head;
+    if (e.mode == HEAD_PLMS_FIRST) {
+      // keep eps in the ring (it becomes noise_list[-1]); x is NOT advanced, only the operand plane
+      *reinterpret_cast<float4*>(e.hist + head * hs + idx) = make_float4(eps[0], eps[1], eps[2], eps[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xn[i] = x_pred(x[i], eps[i], dA, cx, ce);
+      plane_store4(e.XIN, idx, xn);
+      return;
+    }
+    float ep[4];
+    if (e.mode == HEAD_PLMS_SECOND) {
+      const float4 e0 = *reinterpret_cast<const float4*>(e.hist + head * hs + idx);
+      const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ep[i] = div_rn(add_rn(e0a[i], eps[i]), 2.0f);
+    } else {
+      const int nh = e.st->n_hist;
+      *reinterpret_cast<float4*>(e.hist + head * hs + idx) = make_float4(eps[0], eps[1], eps[2], eps[3]);
+      const float4 h1v = *reinterpret_cast<const float4*>(e.hist + ((head + 3) & 3) * hs + idx);
+      const float h1[4] = {h1v.x, h1v.y, h1v.z, h1v.w};
+      if (nh == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ep[i] = div_rn(sub_rn(mul_rn(3.0f, eps[i]), h1[i]), 2.0f);
+      } else {
+        const float4 h2v = *reinterpret_cast<const float4*>(e.hist + ((head + 2) & 3) * hs + idx);
+        const float h2[4] = {h2v.x, h2v.y, h2v.z, h2v.w};
+        if (nh == 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ep[i] = div_rn(add_rn(sub_rn(mul_rn(23.0f, eps[i]), mul_rn(16.0f, h1[i])), mul_rn(5.0f, h2[i])), 12.0f);
+        } else {
+          const float4 h3v = *reinterpret_cast<const float4*>(e.hist + ((head + 1) & 3) * hs + idx);
+          const float h3[4] = {h3v.x, h3v.y, h3v.z, h3v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ep[i] = div_rn(sub_rn(add_rn(sub_rn(mul_rn(55.0f, eps[i]), mul_rn(59.0f, h1[i])), mul_rn(37.0f, h2[i])),
+                                  mul_rn(9.0f, h3[i])), 24.0f);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = x_pred(x[i], ep[i], dA, cx, ce);
+    *reinterpret_cast<float4*>(e.xs + idx) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    plane_store4(e.XIN, idx, xn);
+  }
+};
+
+// ---- generic affine epilogue for the vocoder and the one-off tables ---------------------------
+//   v = acc + bias[n];  v = act(v);  v = v + res[idx];  v = accum[idx] + v;  v = v / div;  out[idx] = v
+struct EpiAffine {
+  static constexpr bool kPair = false;
+  enum Act : int { ACT_NONE = 0, ACT_MISH = 1 };
+  struct Params {
+    const float* bias;   // [Cout] or null
+    const float* res;    // same indexing as out, or null
+    float* out;          // [B][Lout][Cout]
+    int Lout, Cout;
+    int accumulate;      // out = out + v (read-modify-write)
+    float div;           // 1.0f = none
+    int act;
+  };
+  __device__ static __forceinline__ void apply(const Params& e, int b, int op, int n, const float (&a)[4]) {
+    float v[4] = {a[0], a[1], a[2], a[3]};
+    if (e.bias) {
+      const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+      v[0] += bi.x; v[1] += bi.y; v[2] += bi.z; v[3] += bi.w;
+    }
+    if (e.act == ACT_MISH) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = mishf_(v[i]);
+    }
+    const size_t idx = ((size_t)b * e.Lout + op) * e.Cout + n;
+    if (e.res) {
+      const float4 rr = *reinterpret_cast<const float4*>(e.res + idx);
+      v[0] = add_rn(v[0], rr.x); v[1] = add_rn(v[1], rr.y); v[2] = add_rn(v[2], rr.z); v[3] = add_rn(v[3], rr.w);
+    }
+    if (e.accumulate) {
+      const float4 oo = *reinterpret_cast<const float4*>(e.out + idx);
+      v[0] = add_rn(oo.x, v[0]); v[1] = add_rn(oo.y, v[1]); v[2] = add_rn(oo.z, v[2]); v[3] = add_rn(oo.w, v[3]);
+    }
+    if (e.div != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = div_rn(v[i], e.div);
+    }
+    *reinterpret_cast<float4*>(e.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+}  // namespace dsvc

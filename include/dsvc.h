@@ -1,0 +1,206 @@
+/*
+ * dsvc.h -- C-ABI of the B200-native diffusion-SVC inference hot path (libdsvc.so).
+ *
+ * The reference (prophesier/diff-svc) has no FFI: its plug-in surface for this path is a set of
+ * Python classes.  Each entry point below names the reference call site it replaces
+ * (file:line into the reference tree); the Python host mirror in diffsvc_b200/ binds them with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw pointers, ints.  No torch / C++ types cross this boundary.
+ *   - every call returns 0 on success, a negative DSVC_E* code otherwise; dsvc_last_error()
+ *     returns a thread-local human-readable message for the last failure.
+ *   - "host" pointers are read during the call only.  "device" pointers are caller-owned device
+ *     memory (e.g. PyTorch storage) valid on `stream`; the library never frees or reallocates
+ *     them, allocates no caller-visible memory and never synchronises the device implicitly,
+ *     except dsvc_*_create / dsvc_diffnet_prepare which (re)allocate private workspace.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - there is NO CPU fallback: every compute entry point fails with DSVC_ENODEVICE when no
+ *     sm_100 device is present.
+ *   - one in-flight call per handle (the reference is not re-entrant either:
+ *     infer_tools/infer_tool.py, flask_api.py:54 threaded=False).
+ */
+#ifndef DSVC_H_
+#define DSVC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSVC_OK          0
+#define DSVC_EINVAL     -1   /* bad argument / unsupported shape */
+#define DSVC_ECUDA      -2   /* CUDA runtime / driver error */
+#define DSVC_ENODEVICE  -3   /* no sm_100 device: the product path has no CPU fallback */
+#define DSVC_ESTATE     -4   /* call out of order (e.g. eval before prepare) */
+
+/* arithmetic of the 20-layer WaveNet contractions */
+#define DSVC_MATH_TC3F16   0  /* tcgen05 tensor cores, error-compensated fp16 hi/lo split, 3 MMAs per
+                                 product, fp32 accumulate in TMEM: fp32-class results (default) */
+#define DSVC_MATH_FP32     1  /* fp32 FFMA kernels (any channel count; validation + odd shapes) */
+#define DSVC_MATH_TC1F16   2  /* tcgen05, single fp16 pass: "fast mode", NOT within the parity gate */
+
+const char* dsvc_version(void);
+const char* dsvc_last_error(void);
+/* number of sm_100 devices visible (0 on a CPU-only box); never fails */
+int dsvc_device_count(void);
+/* cumulative number of kernels this library launched in this process (bench.py "gpu_launches") */
+uint64_t dsvc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * DiffNet denoiser + Gaussian-diffusion samplers
+ * replaces network/diff/net.py:86-135 (DiffNet), :58-84 (ResidualBlock) and the sampling loop
+ * network/diff/diffusion.py:146-198, :269-278.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dsvc_diffnet dsvc_diffnet_t;
+
+typedef struct {
+  int32_t mel_bins;              /* M: in_dims (net.py:87)                       */
+  int32_t residual_channels;     /* C: hparams['residual_channels'] (net.py:93)  */
+  int32_t encoder_hidden;        /* H: hparams['hidden_size'] (net.py:91)        */
+  int32_t residual_layers;       /* L: hparams['residual_layers'] (net.py:92)    */
+  int32_t dilation_cycle_length; /* hparams['dilation_cycle_length'] (net.py:94) */
+  int32_t num_timesteps;         /* rows of the schedule / step tables           */
+  int32_t math;                  /* DSVC_MATH_*                                   */
+} dsvc_diffnet_config;
+
+/* All weights are HOST fp32 pointers in the reference's state_dict layouts;
+ * per-layer arrays are indexed [residual_layers]. */
+typedef struct {
+  const float* input_projection_w;        /* [C, M, 1]   */
+  const float* input_projection_b;        /* [C]         */
+  const float* mlp0_w;                    /* [4C, C]     */
+  const float* mlp0_b;                    /* [4C]        */
+  const float* mlp2_w;                    /* [C, 4C]     */
+  const float* mlp2_b;                    /* [C]         */
+  const float* const* dilated_conv_w;     /* L x [2C, C, 3] */
+  const float* const* dilated_conv_b;     /* L x [2C]    */
+  const float* const* diffusion_proj_w;   /* L x [C, C]  */
+  const float* const* diffusion_proj_b;   /* L x [C]     */
+  const float* const* conditioner_proj_w; /* L x [2C, H, 1] */
+  const float* const* conditioner_proj_b; /* L x [2C]    */
+  const float* const* output_proj_w;      /* L x [2C, C, 1] */
+  const float* const* output_proj_b;      /* L x [2C]    */
+  const float* skip_projection_w;         /* [C, C, 1]   */
+  const float* skip_projection_b;         /* [C]         */
+  const float* output_projection_w;       /* [M, C, 1]   */
+  const float* output_projection_b;       /* [M]         */
+  /* SinusoidalPosEmb(t) for t = 0..num_timesteps-1, [num_timesteps, C] (net.py:37-44).  The host
+   * evaluates this weight-free basis with the reference's own float ops so that the table is
+   * bit-identical; the MLP and the per-layer diffusion projections (net.py:99-103, :67) run on
+   * the device at create time and are cached as a [num_timesteps, L, C] table. */
+  const float* step_basis;
+} dsvc_diffnet_weights;
+
+/* DiffNet.__init__ + load_state_dict (net.py:87-110).  Uploads and repacks the weights. */
+int dsvc_diffnet_create(dsvc_diffnet_t** out, const dsvc_diffnet_config* cfg,
+                        const dsvc_diffnet_weights* w, void* stream);
+void dsvc_diffnet_destroy(dsvc_diffnet_t* h);
+
+/* The registered schedule buffers of GaussianDiffusion (diffusion.py:102-120), host fp32
+ * [num_timesteps] each.  Taken from the module's buffers (i.e. the checkpoint), never recomputed. */
+int dsvc_diffnet_set_schedule(dsvc_diffnet_t* h,
+                              const float* sqrt_recip_alphas_cumprod,
+                              const float* sqrt_recipm1_alphas_cumprod,
+                              const float* posterior_mean_coef1,
+                              const float* posterior_mean_coef2,
+                              const float* posterior_log_variance_clipped,
+                              const float* alphas_cumprod);
+
+/* Per-utterance (batch) setup: sizes the private workspace for [B, Tmax] and computes the
+ * step-invariant conditioner projections of all L layers once (net.py:68, hoisted out of the
+ * T-step loop).  cond: device fp32 [B, H, Tmax] (= ret['decoder_inp'].transpose(1,2),
+ * diffusion.py:232-234).  lengths: host int32 [B] valid frames per item (NULL = all Tmax); each
+ * item is computed as if alone (its own length is the zero-padding boundary of every conv). */
+int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32_t* lengths,
+                         const float* cond, void* stream);
+
+/* denoise_fn(x, t, cond=cond) (net.py:112-135; called at diffusion.py:147,182,186).
+ * spec, out: device fp32 [B, 1, M, Tmax]; all items share the integer step t. */
+int dsvc_diffnet_eval(dsvc_diffnet_t* h, const float* spec, int32_t t, float* out, void* stream);
+
+/* for i in reversed(range(0, t_start)): x = p_sample(x, i, cond)   (diffusion.py:276-278,
+ * p_sample :157-163, p_mean_variance :146-154).  x: device fp32 [B,1,M,Tmax], updated in place.
+ * noise: device fp32 [t_start, B, 1, M, Tmax] in consumption order (one draw per step including
+ * the masked t==0 draw, diffusion.py:160) or NULL to draw N(0,1) from the library's counter-based
+ * Philox generator keyed by `seed`. */
+int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* noise,
+                     uint64_t seed, void* stream);
+
+/* for i in reversed(range(0, t_start, interval)): x = p_sample_plms(x, i, interval, cond)
+ * (diffusion.py:269-275, p_sample_plms :166-198).  The eps history (noise_list, :96,:270) is
+ * reset at entry and lives in the handle. */
+int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t interval, void* stream);
+
+/* Measurement hook (bench.py roofline): enqueue `iters` back-to-back launches of one kernel of the
+ * WaveNet layer `layer` on the prepared workspace.  part 0 = dilated conv + conditioner + gate
+ * (net.py:69-77), part 1 = output projection + residual + skip (net.py:79-84).  The workspace
+ * contents afterwards are unspecified (call prepare / a sampler again before trusting results). */
+int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NSF-HiFiGAN generator
+ * replaces modules/nsf_hifigan/models.py:325-387 (Generator), :148-323 (SineGen,
+ * SourceModuleHnNSF), :33-64 (ResBlock1), called from network/vocoders/nsf_hifigan.py:36-45,:62-72.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dsvc_nsf dsvc_nsf_t;
+
+#define DSVC_NSF_MAX_STAGES 8
+#define DSVC_NSF_MAX_KERNELS 8
+#define DSVC_NSF_MAX_DILATIONS 8
+
+typedef struct {
+  int32_t num_mels;
+  int32_t sampling_rate;
+  int32_t upsample_initial_channel;
+  int32_t num_upsamples;                                   /* len(h.upsample_rates) */
+  int32_t upsample_rates[DSVC_NSF_MAX_STAGES];
+  int32_t upsample_kernel_sizes[DSVC_NSF_MAX_STAGES];
+  int32_t num_kernels;                                     /* len(h.resblock_kernel_sizes) */
+  int32_t resblock_kernel_sizes[DSVC_NSF_MAX_KERNELS];
+  int32_t num_dilations;                                   /* dilations per ResBlock1 (3) */
+  int32_t resblock_dilation_sizes[DSVC_NSF_MAX_KERNELS][DSVC_NSF_MAX_DILATIONS];
+  int32_t harmonic_num;                                    /* 8 (models.py:334) */
+} dsvc_nsf_config;
+
+/* HOST fp32 pointers, weight-norm already folded (remove_weight_norm, models.py:389-396),
+ * PyTorch layouts. resblocks are indexed [stage * num_kernels + j][dilation m]. */
+typedef struct {
+  const float* source_linear_w;      /* m_source.l_linear.weight [1, harmonic_num+1] */
+  const float* source_linear_b;      /* [1] */
+  const float* conv_pre_w;           /* [C0, num_mels, 7] */
+  const float* conv_pre_b;
+  const float* const* ups_w;         /* stages x [Cin, Cout, K] (ConvTranspose1d layout) */
+  const float* const* ups_b;
+  const float* const* noise_convs_w; /* stages x [Cout, 1, Kn] */
+  const float* const* noise_convs_b;
+  const float* const* convs1_w;      /* (stages*num_kernels*num_dilations) x [ch, ch, k] */
+  const float* const* convs1_b;
+  const float* const* convs2_w;
+  const float* const* convs2_b;
+  const float* conv_post_w;          /* [1, ch_last, 7] */
+  const float* conv_post_b;
+} dsvc_nsf_weights;
+
+int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf_weights* w,
+                    void* stream);
+void dsvc_nsf_destroy(dsvc_nsf_t* h);
+
+/* Generator.forward(x, f0) (models.py:361-387).
+ * mel: device fp32 [B, T, num_mels] log10-mel as produced by the diffusion side; it is scaled by
+ *      `mel_scale` (2.30259: log10 -> ln, nsf_hifigan.py:39,65) on load;
+ * f0:  device fp32 [B, T] in Hz, 0 = unvoiced;
+ * rand_ini: device fp32 [B, harmonic_num+1] replacing torch.rand at models.py:192 (column 0 is
+ *      forced to 0 as at :194), or NULL -> Philox(seed);
+ * sine_noise: device fp32 [B, T*hop, harmonic_num+1] replacing randn_like at models.py:271, or
+ *      NULL -> Philox(seed);
+ * wav: device fp32 [B, T*hop] (= y.view(-1) per item, nsf_hifigan.py:43). */
+int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const float* rand_ini,
+                     const float* sine_noise, uint64_t seed, float mel_scale, float* wav,
+                     int32_t B, int32_t T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSVC_H_ */
