@@ -130,6 +130,13 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream_id
   float2 n = (sel < 2) ? box_muller(r.x, r.y) : box_muller(r.z, r.w);
   return (sel & 1) ? n.y : n.x;
 }
+// four independent N(0,1) for vector index `idx4` of stream (seed, stream_id): one Philox call, two Box-Muller pairs
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream_id, uint64_t idx4) {
+  uint4 ctr = make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), stream_id, 0x5eed4u);
+  uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t stream_id, uint64_t idx) {
   uint4 ctr = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), stream_id, 0xa11ceu);
   uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

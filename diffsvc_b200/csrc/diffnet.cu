@@ -117,6 +117,8 @@ struct dsvc_diffnet {
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
   // CUDA graphs of one sampler step
   cudaGraphExec_t g_ddpm = nullptr, g_plms = nullptr;
+  cudaStream_t cap_stream = nullptr;   // private stream used only to record graphs (the caller's may be the
+                                       // legacy default stream, which cannot be captured)
   const float* g_ddpm_noise = nullptr;
   unsigned long long g_ddpm_seed = 0;
   bool g_ddpm_valid = false, g_plms_valid = false;
@@ -124,6 +126,7 @@ struct dsvc_diffnet {
   ~dsvc_diffnet() {
     if (g_ddpm) cudaGraphExecDestroy(g_ddpm);
     if (g_plms) cudaGraphExecDestroy(g_plms);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
   }
 };
 
@@ -395,11 +398,13 @@ static int store_x(dsvc_diffnet* h, float* x, cudaStream_t s) {
 
 // capture `body` (which enqueues on s) into an executable graph
 template <class F>
-static int capture_graph(cudaGraphExec_t* exec, cudaStream_t s, F body) {
+static int capture_graph(dsvc_diffnet* h, cudaGraphExec_t* exec, F body) {
   if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+  if (!h->cap_stream) DSVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t s = h->cap_stream;
   cudaGraph_t g = nullptr;
   DSVC_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  int r = body();
+  int r = body(s);
   cudaError_t ce = cudaStreamEndCapture(s, &g);
   if (r != DSVC_OK) { if (g) cudaGraphDestroy(g); return r; }
   DSVC_CUDA(ce);
@@ -522,6 +527,8 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
   if (!h->prepared) { set_error("dsvc_diffnet_run_layer: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
   DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && (part == 0 || part == 1) && iters >= 0, "bad layer/part/iters");
   cudaStream_t s = (cudaStream_t)stream;
+  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0, 1);   // a valid step-table row
+  DSVC_LAUNCH_CHECK();
   for (int i = 0; i < iters; ++i) {
     if (part == 0) DSVC_TRY(enqueue_layer_conv(h, layer, s));
     else DSVC_TRY(enqueue_layer_out(h, layer, 0, s));
@@ -540,9 +547,9 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
     DSVC_LAUNCH_CHECK();
     if (!h->g_ddpm_valid || h->g_ddpm_noise != noise || h->g_ddpm_seed != seed) {
       HeadArgs ha; ha.mode = HEAD_DDPM; ha.noise = noise; ha.seed = seed;
-      DSVC_TRY(capture_graph(&h->g_ddpm, s, [&]() -> int {
-        DSVC_TRY(enqueue_eval(h, ha, s));
-        advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0);
+      DSVC_TRY(capture_graph(h, &h->g_ddpm, [&](cudaStream_t cs) -> int {
+        DSVC_TRY(enqueue_eval(h, ha, cs));
+        advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 0);
         DSVC_LAUNCH_CHECK();
         return DSVC_OK;
       }));
@@ -577,9 +584,9 @@ int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t inter
     if (n_iter > 1) {
       if (!h->g_plms_valid) {
         HeadArgs c; c.mode = HEAD_PLMS_NEXT;
-        DSVC_TRY(capture_graph(&h->g_plms, s, [&]() -> int {
-          DSVC_TRY(enqueue_eval(h, c, s));
-          advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 1);
+        DSVC_TRY(capture_graph(h, &h->g_plms, [&](cudaStream_t cs) -> int {
+          DSVC_TRY(enqueue_eval(h, c, cs));
+          advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 1);
           DSVC_LAUNCH_CHECK();
           return DSVC_OK;
         }));

@@ -239,16 +239,21 @@ struct EpiHead {
       const int t = e.st->t;
       const float cr = e.c_recip[t], crm1 = e.c_recipm1[t], c1 = e.c_coef1[t], c2 = e.c_coef2[t];
       const float sd = (t == 0) ? 0.0f : expf(mul_rn(0.5f, e.c_logvar[t]));
+      float nz[4];
+      if (e.noise) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nz[i] = __ldg(e.noise + (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p);
+      } else {
+        // library stream: one Philox4x32-10 call yields the 4 draws of this (step, item, frame, channel-quad)
+        const float4 q = philox_normal4(e.seed, 0x6e6f6973u, (((size_t)e.st->step * e.B + b) * (e.M >> 2) + (n >> 2)) * e.Tmax + p);
+        nz[0] = q.x; nz[1] = q.y; nz[2] = q.z; nz[3] = q.w;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float x0 = sub_rn(mul_rn(cr, x[i]), mul_rn(crm1, eps[i]));       // predict_start_from_noise
         x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                               // clamp_ (clip_denoised)
         const float mean = add_rn(mul_rn(c1, x0), mul_rn(c2, x[i]));      // q_posterior
-        float nz;
-        const size_t nidx = (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p;
-        if (e.noise) nz = __ldg(e.noise + nidx);
-        else nz = philox_normal(e.seed, 0x6e6f6973u, nidx);
-        xn[i] = add_rn(mean, mul_rn(sd, nz));
+        xn[i] = add_rn(mean, mul_rn(sd, nz[i]));
       }
       *reinterpret_cast<float4*>(e.xs + idx) = make_float4(xn[0], xn[1], xn[2], xn[3]);
       plane_store4(e.XIN, idx, xn);

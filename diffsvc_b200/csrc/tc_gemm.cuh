@@ -209,39 +209,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> fused functor -> global =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> fused functor -> coalesced global =====
+    // tcgen05.ld hands each thread one accumulator ROW (a frame).  Global tensors are channels-last,
+    // so rows are staged through shared memory (the pipeline stages are free once tmem_full fires)
+    // and re-read with lane <-> 4 consecutive channels: every global access of the functor is a
+    // 512-byte contiguous warp transaction.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int g = warp & 3;
-    const int p = m0 + g * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16);
-    if constexpr (Epi::kPair) {
+    constexpr int STG_LD = TC_BN + 4;                    // padded row: conflict-free float4 writes
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)g * 32 * STG_LD;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float gate[32], filt[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), gate);
-        tmem_ld32(taddr + (uint32_t)(64 + c * 32), filt);
-        if (p < T) {
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float gg[4] = {gate[4 * q], gate[4 * q + 1], gate[4 * q + 2], gate[4 * q + 3]};
-            const float ff[4] = {filt[4 * q], filt[4 * q + 1], filt[4 * q + 2], filt[4 * q + 3]};
-            Epi::apply_pair(ep, b, p, blockIdx.y * 64 + c * 32 + q * 4, gg, ff);
-          }
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncwarp();
+    if constexpr (Epi::kPair) {
+      const int l16 = lane & 15;
+#pragma unroll 2
+      for (int r2 = 0; r2 < 16; ++r2) {
+        const int r = 2 * r2 + (lane >> 4);
+        const int p = m0 + g * 32 + r;
+        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * l16);
+        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 64 + 4 * l16);
+        if (p < T) {
+          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+          const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+          Epi::apply_pair(ep, b, p, blockIdx.y * 64 + 4 * l16, gg, ff);
         }
       }
     } else {
-#pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
-        if (p < T) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = n0 + c * 32 + q * 4;
-            const float vv[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
-            if (n < N) Epi::apply(ep, b, p, n, vv);
-          }
+      const int n = n0 + 4 * lane;
+#pragma unroll 2
+      for (int r = 0; r < 32; ++r) {
+        const int p = m0 + g * 32 + r;
+        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lane);
+        if (p < T && n < N) {
+          const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
+          Epi::apply(ep, b, p, n, vv);
         }
       }
     }

@@ -169,8 +169,12 @@ def test_plms_chain_full(math_mode):
     sched = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
     ref = O.sample(sd, sched, cond, x0, 1000, None, pndm_speedup=100)
     xf = gd.sample(x0.to(DEV), cond.to(DEV), 1000, 100).cpu()
-    err = (xf - ref).abs().max().item() * 2.5     # normalised units -> mel units (spec_max - spec_min = 5)
-    assert err <= 1e-3, (math_mode, err)
+    # with random weights the 10-iteration PLMS solve is expansive (|x| reaches several hundred in
+    # normalised units; no clamp in PLMS, diffusion.py:166-198), so the bound is relative to the range:
+    # fp32-class agreement = a few 1e-6 of max|x|
+    rng = max(1.0, ref.abs().max().item())
+    err = (xf - ref).abs().max().item() / rng
+    assert err <= 1e-5, (math_mode, err, rng)
 
 
 @pytest.mark.parametrize("math_mode", ["fp32", "tc3f16"])
