@@ -109,9 +109,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or (_stale() and os.path.exists("/usr/local/cuda/bin/nvcc")):
-        build()
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("DSVC_LIB")        # developer override (e.g. an instrumented build)
+    if not path:
+        if not os.path.exists(LIB_PATH) or (_stale() and os.path.exists("/usr/local/cuda/bin/nvcc")):
+            build()
+        path = LIB_PATH
+    lib = C.CDLL(path)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res

@@ -249,8 +249,10 @@ static int tc_build_maps(dsvc_diffnet* h) {
   auto gemm = [&](TcGemmMaps& g, const PlaneBuf& a, int K, const F16Pair& w, int rows) -> int {
     DSVC_TRY(tc_make_a_map(&g.a_hi, a.hi.as<__half>(), B, T, K));
     DSVC_TRY(tc_make_a_map(&g.a_lo, a.lo.as<__half>(), B, T, K));
-    DSVC_TRY(tc_make_b_map(&g.b_hi, w.hi.as<__half>(), rows, K));
-    DSVC_TRY(tc_make_b_map(&g.b_lo, w.lo.as<__half>(), rows, K));
+    DSVC_TRY(tc_make_b_map(&g.b_hi, w.hi.as<__half>(), rows, K, 128));
+    DSVC_TRY(tc_make_b_map(&g.b_lo, w.lo.as<__half>(), rows, K, 128));
+    DSVC_TRY(tc_make_b_map(&g.b32_hi, w.hi.as<__half>(), rows, K, 32));
+    DSVC_TRY(tc_make_b_map(&g.b32_lo, w.lo.as<__half>(), rows, K, 32));
     return DSVC_OK;
   };
   DSVC_TRY(gemm(h->maps.in, h->XIN, M, h->h_in, C));
@@ -533,6 +535,18 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
     if (part == 0) DSVC_TRY(enqueue_layer_conv(h, layer, s));
     else DSVC_TRY(enqueue_layer_out(h, layer, 0, s));
   }
+#ifdef DSVC_TIMELINE
+  if (h->tc) {
+    static long long host_tl[1024][8];
+    DSVC_CUDA(cudaStreamSynchronize(s));
+    DSVC_CUDA(cudaMemcpyFromSymbol(host_tl, g_timeline, sizeof(host_tl)));
+    const int nct = ceil_div(h->Tmax, TC_BM) * ceil_div(2 * h->cfg.residual_channels, 64) * h->B;
+    printf("timeline part %d (cycles since CTA entry): setup | first-operands | mma-issued | epi-prefetch | acc-ready | staged | epi-done\n", part);
+    for (int c = 0; c < nct && c < 1024; c += (nct > 12 ? nct / 12 : 1))
+      printf("  cta %3d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, host_tl[c][0], host_tl[c][1], host_tl[c][2],
+             host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6]);
+  }
+#endif
   return DSVC_OK;
 }
 

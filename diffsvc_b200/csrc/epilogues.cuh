@@ -1,6 +1,10 @@
 // Epilogue functors shared by the fp32 FFMA main loop (simt_gemm.cuh) and the tcgen05 main loop
-// (tc_gemm.cuh).  An epilogue sees one output row (b, op) and a chunk of 4 consecutive output
-// channels n..n+3 with their fp32 accumulators.
+// (tc_gemm.cuh).  An epilogue sees one output row (b, p) and a chunk of 4 consecutive output
+// channels n..n+3 with their fp32 accumulators.  Its global inputs are split in three so that the
+// main loops can batch loads ahead of use (the epilogues are latency-, not bandwidth-bound):
+//   Col  : per-column constants (bias, diffusion-step shift)   -- loaded once per thread
+//   Pre  : per-row inputs (residual stream, skip sum, conditioner projection, sampler state)
+//   l2_prefetch(): the addresses Pre will read, for an early L2 prefetch while the MMAs run
 //
 // Everything the WaveNet layer does besides its two contractions is fused here
 // (reference network/diff/net.py:66-84, :112-135 and network/diff/diffusion.py:146-198).
@@ -27,6 +31,13 @@ struct Plane {
   __half* hi;
   __half* lo;
 };
+
+struct EpiCol { float4 bias; float4 d; };
+struct EpiPre { float4 a; float4 b; };
+
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
@@ -58,16 +69,23 @@ struct EpiInProj {
     int tsel;                // 0: step-table row st->t; 1: st->t_prev (2nd eval of the first PLMS iteration)
     float wscale;            // inverse power-of-two weight scale of the tcgen05 path (1 for FFMA)
   };
-  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
     const int tt = e.tsel ? e.st->t_prev : e.st->t;
-    const float4 d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + 0) * e.C + n));
-    float x[4] = {fmaxf(a[0] * e.wscale + bi.x, 0.f), fmaxf(a[1] * e.wscale + bi.y, 0.f),
-                  fmaxf(a[2] * e.wscale + bi.z, 0.f), fmaxf(a[3] * e.wscale + bi.w, 0.f)};
+    c.d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + 0) * e.C + n));
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params&, int, int, int) {}
+  __device__ static __forceinline__ EpiPre pre(const Params&, int, int, int) { return EpiPre{}; }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre&) {
+    float x[4] = {fmaxf(a[0] * e.wscale + c.bias.x, 0.f), fmaxf(a[1] * e.wscale + c.bias.y, 0.f),
+                  fmaxf(a[2] * e.wscale + c.bias.z, 0.f), fmaxf(a[3] * e.wscale + c.bias.w, 0.f)};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
     *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
     const bool live = p < e.lengths[b];
-    float y[4] = {live ? x[0] + d.x : 0.f, live ? x[1] + d.y : 0.f, live ? x[2] + d.z : 0.f, live ? x[3] + d.w : 0.f};
+    float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
     plane_store4(e.Y, idx, y);
   }
 };
@@ -80,11 +98,19 @@ struct EpiCondProj {
     float* CP;           // [L][B][Tmax][2C]
     int B, Tmax, C2;
   };
-  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params&, int, int, int) {}
+  __device__ static __forceinline__ EpiPre pre(const Params&, int, int, int) { return EpiPre{}; }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre&) {
     const int l = n / e.C2, nn = n - l * e.C2;
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
     const size_t idx = (((size_t)l * e.B + b) * e.Tmax + p) * e.C2 + nn;
-    *reinterpret_cast<float4*>(e.CP + idx) = make_float4(a[0] + bi.x, a[1] + bi.y, a[2] + bi.z, a[3] + bi.w);
+    *reinterpret_cast<float4*>(e.CP + idx) = make_float4(a[0] + c.bias.x, a[1] + c.bias.y, a[2] + c.bias.z, a[3] + c.bias.w);
   }
 };
 
@@ -97,17 +123,27 @@ struct EpiGate {
     int Tmax, C;
     float wscale;
   };
-  __device__ static __forceinline__ void apply_pair(const Params& e, int b, int p, int c0,
-                                                    const float (&g)[4], const float (&f)[4]) {
-    const size_t row = (size_t)b * e.Tmax + p;
-    const float4 cg = __ldg(reinterpret_cast<const float4*>(e.CP + row * (2 * e.C) + c0));
-    const float4 cf = __ldg(reinterpret_cast<const float4*>(e.CP + row * (2 * e.C) + e.C + c0));
-    const float gg[4] = {g[0] * e.wscale + cg.x, g[1] * e.wscale + cg.y, g[2] * e.wscale + cg.z, g[3] * e.wscale + cg.w};
-    const float ff[4] = {f[0] * e.wscale + cf.x, f[1] * e.wscale + cf.y, f[2] * e.wscale + cf.z, f[3] * e.wscale + cf.w};
+  __device__ static __forceinline__ EpiCol col(const Params&, int) { return EpiCol{}; }
+  __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int c0) {
+    const float* row = e.CP + ((size_t)b * e.Tmax + p) * (2 * e.C);
+    l2_prefetch_line(row + c0);
+    l2_prefetch_line(row + e.C + c0);
+  }
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int c0) {
+    const float* row = e.CP + ((size_t)b * e.Tmax + p) * (2 * e.C);
+    EpiPre r;
+    r.a = __ldg(reinterpret_cast<const float4*>(row + c0));
+    r.b = __ldg(reinterpret_cast<const float4*>(row + e.C + c0));
+    return r;
+  }
+  __device__ static __forceinline__ void apply_pair(const Params& e, int b, int p, int c0, const float (&g)[4],
+                                                    const float (&f)[4], const EpiCol&, const EpiPre& r) {
+    const float gg[4] = {g[0] * e.wscale + r.a.x, g[1] * e.wscale + r.a.y, g[2] * e.wscale + r.a.z, g[3] * e.wscale + r.a.w};
+    const float ff[4] = {f[0] * e.wscale + r.b.x, f[1] * e.wscale + r.b.y, f[2] * e.wscale + r.b.z, f[3] * e.wscale + r.b.w};
     float z[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) z[i] = sigmoidf_(gg[i]) * tanhf(ff[i]);
-    plane_store4(e.Z, row * e.C + c0, z);
+    plane_store4(e.Z, ((size_t)b * e.Tmax + p) * e.C + c0, z);
   }
 };
 
@@ -128,29 +164,49 @@ struct EpiOutProj {
     int tsel;
     float wscale;
   };
-  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    const float v[4] = {a[0] * e.wscale + bi.x, a[1] * e.wscale + bi.y, a[2] * e.wscale + bi.z, a[3] * e.wscale + bi.w};
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < e.C && e.layer + 1 < e.L) {
+      const int tt = e.tsel ? e.st->t_prev : e.st->t;
+      c.d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + e.layer + 1) * e.C + n));
+    }
+    return c;
+  }
+  __device__ static __forceinline__ const float* src(const Params& e, int b, int p, int n) {
+    if (n < e.C) return e.X + ((size_t)b * e.Tmax + p) * e.C + n;
+    return e.layer > 0 ? e.S + ((size_t)b * e.Tmax + p) * e.C + (n - e.C) : nullptr;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int n) {
+    const float* s = src(e, b, p, n);
+    if (s) l2_prefetch_line(s);
+  }
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int n) {
+    EpiPre r{};
+    const float* s = src(e, b, p, n);
+    if (s) r.a = *reinterpret_cast<const float4*>(s);
+    return r;
+  }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre& r) {
+    const float v[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     if (n < e.C) {
       const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
-      const float4 xo = *reinterpret_cast<const float4*>(e.X + idx);
       const float s2 = 1.41421356237309504880f;
-      float x[4] = {div_rn(add_rn(xo.x, v[0]), s2), div_rn(add_rn(xo.y, v[1]), s2),
-                    div_rn(add_rn(xo.z, v[2]), s2), div_rn(add_rn(xo.w, v[3]), s2)};
+      float x[4] = {div_rn(add_rn(r.a.x, v[0]), s2), div_rn(add_rn(r.a.y, v[1]), s2),
+                    div_rn(add_rn(r.a.z, v[2]), s2), div_rn(add_rn(r.a.w, v[3]), s2)};
       *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
       if (e.layer + 1 < e.L) {
-        const int tt = e.tsel ? e.st->t_prev : e.st->t;
-        const float4 d = __ldg(reinterpret_cast<const float4*>(e.dtab + ((size_t)tt * e.L + e.layer + 1) * e.C + n));
         const bool live = p < e.lengths[b];
-        float y[4] = {live ? x[0] + d.x : 0.f, live ? x[1] + d.y : 0.f, live ? x[2] + d.z : 0.f, live ? x[3] + d.w : 0.f};
+        float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
         plane_store4(e.Y, idx, y);
       }
     } else {
       const size_t idx = ((size_t)b * e.Tmax + p) * e.C + (n - e.C);
       float s[4] = {v[0], v[1], v[2], v[3]};
       if (e.layer > 0) {
-        const float4 so = *reinterpret_cast<const float4*>(e.S + idx);
-        s[0] = add_rn(so.x, v[0]); s[1] = add_rn(so.y, v[1]); s[2] = add_rn(so.z, v[2]); s[3] = add_rn(so.w, v[3]);
+        s[0] = add_rn(r.a.x, v[0]); s[1] = add_rn(r.a.y, v[1]); s[2] = add_rn(r.a.z, v[2]); s[3] = add_rn(r.a.w, v[3]);
       }
       if (e.layer + 1 < e.L) {
         *reinterpret_cast<float4*>(e.S + idx) = make_float4(s[0], s[1], s[2], s[3]);
@@ -172,10 +228,18 @@ struct EpiSkipProj {
     int Tmax, C;
     float wscale;
   };
-  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    float r[4] = {fmaxf(a[0] * e.wscale + bi.x, 0.f), fmaxf(a[1] * e.wscale + bi.y, 0.f),
-                  fmaxf(a[2] * e.wscale + bi.z, 0.f), fmaxf(a[3] * e.wscale + bi.w, 0.f)};
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params&, int, int, int) {}
+  __device__ static __forceinline__ EpiPre pre(const Params&, int, int, int) { return EpiPre{}; }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre&) {
+    float r[4] = {fmaxf(a[0] * e.wscale + c.bias.x, 0.f), fmaxf(a[1] * e.wscale + c.bias.y, 0.f),
+                  fmaxf(a[2] * e.wscale + c.bias.z, 0.f), fmaxf(a[3] * e.wscale + c.bias.w, 0.f)};
     plane_store4(e.R, ((size_t)b * e.Tmax + p) * e.C + n, r);
   }
 };
@@ -223,21 +287,39 @@ struct EpiHead {
     return add_rn(x, mul_rn(dA, sub_rn(mul_rn(cx, x), mul_rn(ce, eps))));
   }
 
-  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4]) {
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    const float eps[4] = {a[0] * e.wscale + bi.x, a[1] * e.wscale + bi.y, a[2] * e.wscale + bi.z, a[3] * e.wscale + bi.w};
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.mode == HEAD_DDPM) {     // per-step scalars ride in the column context
+      const int t = e.st->t;
+      c.d = make_float4(e.c_recip[t], e.c_recipm1[t], e.c_coef1[t], e.c_coef2[t]);
+    }
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int n) {
+    if (e.mode != HEAD_EVAL) l2_prefetch_line(e.xs + ((size_t)b * e.Tmax + p) * e.M + n);
+  }
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int n) {
+    EpiPre r{};
+    if (e.mode != HEAD_EVAL) r.a = *reinterpret_cast<const float4*>(e.xs + ((size_t)b * e.Tmax + p) * e.M + n);
+    return r;
+  }
+
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre& r) {
+    const float eps[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.M + n;
     if (e.mode == HEAD_EVAL) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) e.out[((size_t)b * e.M + n + i) * e.Tmax + p] = eps[i];
       return;
     }
-    const float4 xo = *reinterpret_cast<const float4*>(e.xs + idx);
-    const float x[4] = {xo.x, xo.y, xo.z, xo.w};
+    const float x[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
     float xn[4];
     if (e.mode == HEAD_DDPM) {
       const int t = e.st->t;
-      const float cr = e.c_recip[t], crm1 = e.c_recipm1[t], c1 = e.c_coef1[t], c2 = e.c_coef2[t];
+      const float cr = c.d.x, crm1 = c.d.y, c1 = c.d.z, c2 = c.d.w;
       const float sd = (t == 0) ? 0.0f : expf(mul_rn(0.5f, e.c_logvar[t]));
       float nz[4];
       if (e.noise) {
@@ -311,7 +393,7 @@ struct EpiHead {
 };
 
 // ---- generic affine epilogue for the vocoder and the one-off tables ---------------------------
-//   v = acc + bias[n];  v = act(v);  v = v + res[idx];  v = accum[idx] + v;  v = v / div;  out[idx] = v
+//   v = acc + bias[n];  v = act(v);  v = v + res[idx];  v = out[idx] + v;  v = v / div;  out[idx] = v
 struct EpiAffine {
   static constexpr bool kPair = false;
   enum Act : int { ACT_NONE = 0, ACT_MISH = 1 };
@@ -324,30 +406,34 @@ struct EpiAffine {
     float div;           // 1.0f = none
     int act;
   };
-  __device__ static __forceinline__ void apply(const Params& e, int b, int op, int n, const float (&a)[4]) {
-    float v[4] = {a[0], a[1], a[2], a[3]};
-    if (e.bias) {
-      const float4 bi = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-      v[0] += bi.x; v[1] += bi.y; v[2] += bi.z; v[3] += bi.w;
-    }
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params&, int, int, int) {}
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int op, int n) {
+    EpiPre r{};
+    const size_t idx = ((size_t)b * e.Lout + op) * e.Cout + n;
+    if (e.res) r.a = *reinterpret_cast<const float4*>(e.res + idx);
+    if (e.accumulate) r.b = *reinterpret_cast<const float4*>(e.out + idx);
+    return r;
+  }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int op, int n, const float (&a)[4],
+                                               const EpiCol& c, const EpiPre& r) {
+    float v[4] = {a[0] + c.bias.x, a[1] + c.bias.y, a[2] + c.bias.z, a[3] + c.bias.w};
     if (e.act == ACT_MISH) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = mishf_(v[i]);
     }
-    const size_t idx = ((size_t)b * e.Lout + op) * e.Cout + n;
-    if (e.res) {
-      const float4 rr = *reinterpret_cast<const float4*>(e.res + idx);
-      v[0] = add_rn(v[0], rr.x); v[1] = add_rn(v[1], rr.y); v[2] = add_rn(v[2], rr.z); v[3] = add_rn(v[3], rr.w);
-    }
-    if (e.accumulate) {
-      const float4 oo = *reinterpret_cast<const float4*>(e.out + idx);
-      v[0] = add_rn(oo.x, v[0]); v[1] = add_rn(oo.y, v[1]); v[2] = add_rn(oo.z, v[2]); v[3] = add_rn(oo.w, v[3]);
-    }
+    if (e.res) { v[0] = add_rn(v[0], r.a.x); v[1] = add_rn(v[1], r.a.y); v[2] = add_rn(v[2], r.a.z); v[3] = add_rn(v[3], r.a.w); }
+    if (e.accumulate) { v[0] = add_rn(r.b.x, v[0]); v[1] = add_rn(r.b.y, v[1]); v[2] = add_rn(r.b.z, v[2]); v[3] = add_rn(r.b.w, v[3]); }
     if (e.div != 1.0f) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = div_rn(v[i], e.div);
     }
-    *reinterpret_cast<float4*>(e.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(e.out + ((size_t)b * e.Lout + op) * e.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
 

@@ -12,6 +12,7 @@
 // (tc_gemm.cuh) shares the epilogue functors.
 #pragma once
 #include "common.cuh"
+#include "epilogues.cuh"
 
 namespace dsvc {
 
@@ -206,26 +207,42 @@ conv_gemm_f32_kernel(const ConvGemmParams p, const typename Epi::Params ep) {
   }
 
   // ---- epilogue: each thread owns TM rows x (one or two) 4-column chunks ----
+  if constexpr (Epi::kPair) {
+    const int c0 = blockIdx.y * (BN / 2) + tx * 4;   // pair-channel index
+    const EpiCol cc = Epi::col(ep, c0);
+    EpiPre pre[TM];
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int pr = p0 + ty * TM + i;
-    if (pr >= p.rows) continue;
-    const int op = (p.nphase > 1) ? pr * p.nphase + r : pr;
-    if constexpr (Epi::kPair) {
+    for (int i = 0; i < TM; ++i) {
+      const int pr = p0 + ty * TM + i;
+      if (pr < p.rows) pre[i] = Epi::pre(ep, b, pr, c0);
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int pr = p0 + ty * TM + i;
+      if (pr >= p.rows) continue;
       float g[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
       float f[4] = {acc[i][4], acc[i][5], acc[i][6], acc[i][7]};
-      const int c0 = blockIdx.y * (BN / 2) + tx * 4;   // pair-channel index
-      Epi::apply_pair(ep, b, op, c0, g, f);
-    } else {
-      {
-        const int n = n0 + tx * 4;
-        float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
-        if (n < p.Cout) Epi::apply(ep, b, op, n, v);
+      Epi::apply_pair(ep, b, pr, c0, g, f, cc, pre[i]);
+    }
+  } else {
+#pragma unroll
+    for (int h2 = 0; h2 < TN / 4; ++h2) {
+      const int n = n0 + tx * 4 + h2 * (BN / 2);
+      if (n >= p.Cout) continue;
+      const EpiCol cc = Epi::col(ep, n);
+      EpiPre pre[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int pr = p0 + ty * TM + i;
+        if (pr < p.rows) pre[i] = Epi::pre(ep, b, (p.nphase > 1) ? pr * p.nphase + r : pr, n);
       }
-      if constexpr (TN == 8) {
-        const int n = n0 + tx * 4 + BN / 2;
-        float v[4] = {acc[i][4], acc[i][5], acc[i][6], acc[i][7]};
-        if (n < p.Cout) Epi::apply(ep, b, op, n, v);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int pr = p0 + ty * TM + i;
+        if (pr >= p.rows) continue;
+        const int op = (p.nphase > 1) ? pr * p.nphase + r : pr;
+        float v[4] = {acc[i][4 * h2], acc[i][4 * h2 + 1], acc[i][4 * h2 + 2], acc[i][4 * h2 + 3]};
+        Epi::apply(ep, b, op, n, v, cc, pre[i]);
       }
     }
   }

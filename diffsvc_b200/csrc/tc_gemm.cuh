@@ -4,28 +4,37 @@
 //
 // A: activation plane, channels-last fp16 (hi, lo) pair [B][T][K]  (K-major)
 // W: weight matrix fp16 (hi, lo) pair [taps*N][K]                  (K-major)
-// One CTA owns a 128-frame x 128-channel output tile.  Operands are staged by TMA into 128B-swizzled
-// shared memory (the shifted tap is just a different TMA frame coordinate; out-of-range frames are
-// zero-filled by the TMA unit = the conv's zero padding), multiplied by tcgen05.mma (M=128, N=128,
-// K=16 per instruction, fp32 accumulators in TMEM) and read back with tcgen05.ld by four epilogue
-// warps that run the fused epilogue functor (epilogues.cuh) straight out of registers.
+// One CTA owns a 128-frame x BN-channel output tile (BN = 128, or 64 when the grid would otherwise
+// leave most of the 148 SMs idle).  Operands are staged by TMA into 128B-swizzled shared memory (the
+// shifted tap is just a different TMA frame coordinate; out-of-range frames are zero-filled by the TMA
+// unit = the conv's zero padding), multiplied by tcgen05.mma (M=128, N=BN, K=16 per instruction, fp32
+// accumulators in TMEM) and read back with tcgen05.ld by all 16 warps, which run the fused epilogue
+// functor (epilogues.cuh) on a shared-memory transpose of the tile.
 //
 // fp32-class accuracy on fp16 tensor cores: x = xh + xl, w = wh + wl (each fp16), and
 //   x*w ~= xh*wh + xl*wh + xh*wl      (3 MMAs into the same fp32 accumulator; the dropped xl*wl
 //                                      term is ~2^-22 relative)
 // `passes == 1` issues only xh*wh ("fast mode", outside the parity gate).
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM lane group = warp % 4).
+// Warp roles (512 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
+// allocator; all 16 warps then run the epilogue (TMEM lane quarter = warp % 4, BN/4 columns each).
+//
+// Launched with programmatic dependent launch: the prologue (barrier init, TMEM alloc, tensor-map
+// prefetch, weight-tile TMA) overlaps the tail of the previous kernel; everything that reads data the
+// previous kernel wrote sits behind griddepcontrol.wait.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "epilogues.cuh"
 
 namespace dsvc {
 
 struct TcGemmMaps {
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap a_hi, a_lo;        // activation planes, box {64 ch, 128 frames, 1 item}
+  CUtensorMap b_hi, b_lo;        // weights, box {64, 128 rows}   (BN = 128 tiles)
+  CUtensorMap b32_hi, b32_lo;    // weights, box {64, 32 rows}    (BN = 64 tiles: two boxes per stage)
 };
 struct TcMaps {
   TcGemmMaps in, skip, head;
@@ -33,12 +42,16 @@ struct TcMaps {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BN = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;            // 16 KB: one [128 rows][64 fp16] tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int TC_THREADS = 512;
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB: one [128 rows][64 fp16] tile
+
+template <int BN> struct TcCfg {
+  static constexpr int B_TILE = BN * TC_BK * 2;
+  static constexpr int STAGE = 2 * (TC_A_TILE + B_TILE);     // A_hi, A_lo, B_hi, B_lo
+  static constexpr int STAGES = (BN == 64) ? 4 : 3;           // 192 KB of operands in flight either way
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 128 /*barriers*/;
+};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +90,8 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -114,25 +129,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int CW> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&r)[CW]);
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float (&r)[32]) { tmem_ld32(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&r)[16]) { tmem_ld16(taddr, r); }
+
+// ---- optional per-CTA timeline (cycles since kernel entry), build with -DDSVC_TIMELINE ----------
+#ifdef DSVC_TIMELINE
+__device__ long long g_timeline[1024][8];
+#define TL_MARK(slot) do { if (lane == 0) g_timeline[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 1023][slot] = clock64() - tl0; } while (0)
+#else
+#define TL_MARK(slot) do { } while (0)
+#endif
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <class Epi>
-__global__ void __launch_bounds__(256, 1)
+template <class Epi, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  pdl_launch_dependents();                   // let the next kernel's prologue start early
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
-  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * TC_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 1);
-  auto tile = [&](int s, int which) { return smem_base + (uint32_t)s * TC_STAGE_BYTES + (uint32_t)which * TC_TILE_BYTES; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  // stage layout: [A_hi 16K][A_lo 16K][B_hi][B_lo]
+  auto tile_a = [&](int s, int lo) { return smem_base + (uint32_t)s * Cfg::STAGE + (uint32_t)lo * TC_A_TILE; };
+  auto tile_b = [&](int s, int lo) { return smem_base + (uint32_t)s * Cfg::STAGE + 2u * TC_A_TILE + (uint32_t)lo * Cfg::B_TILE; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN, b = blockIdx.z;
+#ifdef DSVC_TIMELINE
+  const long long tl0 = clock64();
+#endif
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int kblocks = K / TC_BK;
   const int total = taps * kblocks;
   const bool three = passes == 3;
@@ -146,7 +190,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -154,7 +198,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TC_BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -162,38 +206,70 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (warp == 3) TL_MARK(0);   // setup done
+
+  // weight tile(s) of pipeline iteration `it` into stage s (weights are constants: no dependency on
+  // the previous kernel, so the first STAGES of them are requested before griddepcontrol.wait)
+  auto load_b = [&](int it, int s) {
+    const int tap = it / kblocks, kb = it - tap * kblocks;
+    const int row = tap * N + n0;
+    if constexpr (BN == 128) {
+      tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0), kb * TC_BK, row);
+      if (three) tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1), kb * TC_BK, row);
+    } else {
+      // two 32-row boxes.  Pair (gate|filter) tiles live in a 128-row super-tile packed as
+      // [64 gate rows | 64 filter rows]: tile h of super-tile j takes gate rows 128j+32h and
+      // filter rows 128j+64+32h.  Plain tiles take rows n0 and n0+32.
+      const int r0 = Epi::kPair ? tap * N + (int)(blockIdx.y >> 1) * 128 + (int)(blockIdx.y & 1) * 32 : row;
+      const int r1 = Epi::kPair ? r0 + 64 : row + 32;
+      tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0), kb * TC_BK, r0);
+      tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0) + 32u * 128u, kb * TC_BK, r1);
+      if (three) {
+        tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1), kb * TC_BK, r0);
+        tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1) + 32u * 128u, kb * TC_BK, r1);
+      }
+    }
+  };
+  auto load_a = [&](int it, int s) {
+    const int tap = it / kblocks, kb = it - tap * kblocks;
+    const int frame = m0 + (taps == 3 ? (tap - 1) * dil : 0);
+    tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
+    if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const uint32_t tx_bytes = three ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2;
-      for (int it = 0; it < total; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+      const uint32_t tx_bytes = three ? Cfg::STAGE : Cfg::STAGE / 2;
+      const int pre = total < STAGES ? total : STAGES;
+      for (int it = 0; it < pre; ++it) {        // stages are initially free: no empty-wait needed
+        mbar_expect_tx(full_bar(it), tx_bytes);
+        load_b(it, it);
+      }
+      pdl_wait();                               // activations below were written by the previous kernel
+      for (int it = 0; it < pre; ++it) load_a(it, it);
+      for (int it = pre; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const int tap = it / kblocks, kb = it - tap * kblocks;
-        const int frame = m0 + (taps == 3 ? (tap - 1) * dil : 0);
         mbar_expect_tx(full_bar(s), tx_bytes);
-        tma_load_3d(&tmAh, full_bar(s), tile(s, 0), kb * TC_BK, frame, b);
-        tma_load_2d(&tmBh, full_bar(s), tile(s, 2), kb * TC_BK, tap * N + n0);
-        if (three) {
-          tma_load_3d(&tmAl, full_bar(s), tile(s, 1), kb * TC_BK, frame, b);
-          tma_load_2d(&tmBl, full_bar(s), tile(s, 3), kb * TC_BK, tap * N + n0);
-        }
+        load_a(it, s);
+        load_b(it, s);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_f16(TC_BM, TC_BN);
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
       for (int it = 0; it < total; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
+        if (it == 0) TL_MARK(1);            // first operands landed
         tc_fence_after();
-        const uint64_t ah = umma_desc_sw128(tile(s, 0)), al = umma_desc_sw128(tile(s, 1));
-        const uint64_t bh = umma_desc_sw128(tile(s, 2)), bl = umma_desc_sw128(tile(s, 3));
+        const uint64_t ah = umma_desc_sw128(tile_a(s, 0)), al = umma_desc_sw128(tile_a(s, 1));
+        const uint64_t bh = umma_desc_sw128(tile_b(s, 0)), bl = umma_desc_sw128(tile_b(s, 1));
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
           const uint64_t koff = (uint64_t)((k4 * 32) >> 4);   // +32 B per K=16 step inside the swizzled row
@@ -206,61 +282,88 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         umma_commit(empty_bar(s));          // frees the smem stage once these MMAs have read it
       }
       umma_commit(tmem_full_bar);           // accumulator complete
+      TL_MARK(2);                           // all MMAs issued
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> smem transpose -> fused functor -> coalesced global =====
-    // tcgen05.ld hands each thread one accumulator ROW (a frame).  Global tensors are channels-last,
-    // so rows are staged through shared memory (the pipeline stages are free once tmem_full fires)
-    // and re-read with lane <-> 4 consecutive channels: every global access of the functor is a
-    // 512-byte contiguous warp transaction.
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int g = warp & 3;
-    const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16);
-    constexpr int STG_LD = TC_BN + 4;                    // padded row: conflict-free float4 writes
-    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)g * 32 * STG_LD;
-#pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(taddr + (uint32_t)(c * 32), v);
+  }
+  pdl_wait();   // every thread: the epilogue reads tensors the previous kernel wrote
+  {
+    // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
+    // tcgen05.ld hands each thread one accumulator ROW (a frame); a warp may only touch the TMEM lane
+    // quarter (warp % 4).  Global tensors are channels-last, so the four warps of a quarter stage their
+    // 32 x BN/4 blocks into one [32 rows][BN cols] shared-memory slab (the pipeline stages are free once
+    // tmem_full fires), then each takes 8 rows with lane <-> 4 consecutive channels: every global access
+    // of the functor is a contiguous warp transaction, and the transcendental-heavy gating runs on 16
+    // warps instead of 4.
+    constexpr int LPR = Epi::kPair ? BN / 8 : BN / 4;     // lanes per row
+    constexpr int RPI = 32 / LPR;                         // rows per iteration
+    constexpr int NIT = 8 / RPI;                          // iterations for this warp's 8 rows
+    constexpr int CW = BN / 4;                            // columns staged by this warp
+    const int q = warp & 3;                      // TMEM lane quarter = rows 32q .. 32q+31 of the tile
+    const int cg = warp >> 2;                    // column group staged by this warp; also its row octet
+    const int lc = lane % LPR, rsub = lane / LPR;
+    const int ncol = Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * lc : n0 + 4 * lc;   // this lane's 4 channels
+    const bool col_ok = Epi::kPair ? true : (ncol < N);
+    const int row0 = q * 32 + cg * 8;            // first of this warp's 8 rows (tile-relative)
+    // While the MMAs run: pull the rows this warp's epilogue will read into L2 (one request per 128-B line)
+    if (col_ok && (lc & 7) == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(stg + lane * STG_LD + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int i = 0; i < NIT; ++i) {
+        const int p = m0 + row0 + i * RPI + rsub;
+        if (p < T) Epi::l2_prefetch(ep, b, p, ncol);
+      }
     }
-    __syncwarp();
-    if constexpr (Epi::kPair) {
-      const int l16 = lane & 15;
-#pragma unroll 2
-      for (int r2 = 0; r2 < 16; ++r2) {
-        const int r = 2 * r2 + (lane >> 4);
-        const int p = m0 + g * 32 + r;
-        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * l16);
-        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 64 + 4 * l16);
+    EpiCol cc{};
+    if (col_ok) cc = Epi::col(ep, ncol);
+    if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
+    mbar_wait(tmem_full_bar, 0);
+    if (warp == 4) TL_MARK(4);             // accumulator ready
+    tc_fence_after();
+    constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
+    float* slab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)q * 32 * STG_LD;
+    {
+      float v[CW];
+      tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW), v);
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j)
+        *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
+    if (warp == 4) TL_MARK(5);             // staged to smem
+    const float* stg = slab + (size_t)(cg * 8) * STG_LD;
+    EpiPre pre[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int p = m0 + row0 + i * RPI + rsub;
+      if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int r = i * RPI + rsub;
+      const int p = m0 + row0 + r;
+      if constexpr (Epi::kPair) {
+        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
+        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + BN / 2 + 4 * lc);
         if (p < T) {
           const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
           const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
-          Epi::apply_pair(ep, b, p, blockIdx.y * 64 + 4 * l16, gg, ff);
+          Epi::apply_pair(ep, b, p, ncol, gg, ff, cc, pre[i]);
         }
-      }
-    } else {
-      const int n = n0 + 4 * lane;
-#pragma unroll 2
-      for (int r = 0; r < 32; ++r) {
-        const int p = m0 + g * 32 + r;
-        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lane);
-        if (p < T && n < N) {
+      } else {
+        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
+        if (p < T && col_ok) {
           const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
-          Epi::apply(ep, b, p, n, vv);
+          Epi::apply(ep, b, p, ncol, vv, cc, pre[i]);
         }
       }
     }
   }
+  if (warp == 4) TL_MARK(6);               // epilogue done
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
 #endif
 }
@@ -299,13 +402,13 @@ static inline int tc_make_a_map(CUtensorMap* m, const __half* base, int B, int T
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A [%d][%d][%d]) failed: %d", B, T, K, (int)r); return DSVC_ECUDA; }
   return DSVC_OK;
 }
-// weight matrix [rows][K] fp16, box = {64, 128 rows}
-static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, int K) {
+// weight matrix [rows][K] fp16, box = {64, box_rows}
+static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows) {
   PFN_encodeTiled enc;
   DSVC_TRY(tc_encode_fn(&enc));
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {TC_BK, TC_BN};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -313,19 +416,54 @@ static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, in
   return DSVC_OK;
 }
 
+inline bool tc_use_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DSVC_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+template <class Epi, int BN>
+int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
+                 cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = tc_gemm_kernel<Epi, BN>;
+  if (!attr_set) {
+    DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ceil_div(T, TC_BM), ceil_div(N, BN), B);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_use_pdl() ? 1 : 0;
+  const CUtensorMap& bh = (BN == 128) ? m.b_hi : m.b32_hi;
+  const CUtensorMap& bl = (BN == 128) ? m.b_lo : m.b32_lo;
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, passes));
+  DSVC_LAUNCH_CHECK();
+  return DSVC_OK;
+}
+
+// 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
+// 1.7+ waves the narrower tiles re-fetch the activation tile twice as often and lose ~35 %)
+inline bool tc_narrow_tiles(int B, int T, int N) {
+  static int forced = -2;
+  if (forced == -2) { const char* e = getenv("DSVC_TC_BN"); forced = e ? atoi(e) : -1; }
+  if (forced == 64) return true;
+  if (forced == 128) return false;
+  return (long long)ceil_div(T, TC_BM) * ceil_div(N, 128) * B < 148;
+}
+
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
               cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
-  dim3 grid(ceil_div(T, TC_BM), ceil_div(N, TC_BN), B);
-  tc_gemm_kernel<Epi><<<grid, 256, TC_SMEM_BYTES, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, e, T, K, N, taps, dil, passes);
-  DSVC_LAUNCH_CHECK();
-  return DSVC_OK;
+  if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s);
+  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s);
 }
 
 }  // namespace dsvc
