@@ -1,7 +1,10 @@
 """Vocoder registry / plug-in API: network/vocoders/base_vocoder.py:2-39."""
 import importlib
 
-VOCODERS = {}
+try:  # drop-in: share the reference's registry so get_vocoder_cls() in infer_tool finds our classes
+    from network.vocoders.base_vocoder import VOCODERS  # type: ignore
+except Exception:
+    VOCODERS = {}
 
 
 def register_vocoder(cls):
