@@ -9,6 +9,12 @@ for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
         sys.path.insert(0, p)
 
 
+def pytest_sessionstart(session):
+    # many-core hosts (the GPU box has 128 hardware threads) oversubscribe badly on the oracle's small convs
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
