@@ -4,6 +4,7 @@
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
 #include "tc_gemm.cuh"
+#include "tc_conv3.cuh"
 
 #include <cmath>
 #include <memory>
@@ -262,6 +263,8 @@ static int tc_build_maps(dsvc_diffnet* h) {
   h->maps.out.resize(L);
   for (int l = 0; l < L; ++l) {
     DSVC_TRY(gemm(h->maps.dil[l], h->Y, C, *h->h_dil[l], 3 * 2 * C));
+    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_hi, h->Y.hi.as<__half>(), B, T, C));
+    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_lo, h->Y.lo.as<__half>(), B, T, C));
     DSVC_TRY(gemm(h->maps.out[l], h->Z, C, *h->h_out[l], 2 * C));
   }
   return DSVC_OK;
@@ -301,7 +304,13 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
   e.CP = h->CP.as<float>() + (size_t)l * B * T * 2 * C; e.Z = h->Z.view(tc); e.Tmax = T; e.C = C;
   if (tc) {
     e.wscale = h->h_dil[l]->inv_scale;
-    return tc_launch<EpiGate>(h->maps.dil[l], e, B, T, C, 2 * C, 3, dil, h->passes, s);
+    const TcGemmMaps& m = h->maps.dil[l];
+    if (tc_use_halo() && dil <= TC3_HALO) {   // one activation tile per K-block shared by the three taps
+      if (tc_narrow_tiles(B, T, 2 * C))
+        return tc3_launch_bn<EpiGate, 64>(m.a144_hi, m.a144_lo, m.b32_hi, m.b32_lo, e, B, T, C, 2 * C, dil, h->passes, s);
+      return tc3_launch_bn<EpiGate, 128>(m.a144_hi, m.a144_lo, m.b_hi, m.b_lo, e, B, T, C, 2 * C, dil, h->passes, s);
+    }
+    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s);
   }
   e.wscale = 1.f;
   const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;

@@ -35,6 +35,7 @@ struct TcGemmMaps {
   CUtensorMap a_hi, a_lo;        // activation planes, box {64 ch, 128 frames, 1 item}
   CUtensorMap b_hi, b_lo;        // weights, box {64, 128 rows}   (BN = 128 tiles)
   CUtensorMap b32_hi, b32_lo;    // weights, box {64, 32 rows}    (BN = 64 tiles: two boxes per stage)
+  CUtensorMap a144_hi, a144_lo;  // dilated-conv layers only: box {64 ch, 144 frames} (tc_conv3.cuh)
 };
 struct TcMaps {
   TcGemmMaps in, skip, head;
@@ -90,6 +91,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp (the compiler then emits straight-line uniform-datapath code for the
+// TMA / MMA issue instead of per-instruction ELECT + BRA.U.ANY serialisation loops)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -151,6 +163,92 @@ __device__ long long g_timeline[1024][8];
 #define TL_MARK(slot) do { } while (0)
 #endif
 
+// ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
+template <class Epi, int BN>
+__device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint8_t* smem_raw, uint32_t smem_base,
+                                            uint32_t tmem_base, uint32_t tmem_full_bar, int T, int N, int m0, int n0,
+                                            int b, int warp, int lane, bool two_acc
+#ifdef DSVC_TIMELINE
+                                            , long long tl0
+#endif
+) {
+    // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
+    // tcgen05.ld hands each thread one accumulator ROW (a frame); a warp may only touch the TMEM lane
+    // quarter (warp % 4).  Global tensors are channels-last, so the four warps of a quarter stage their
+    // 32 x BN/4 blocks into one [32 rows][BN cols] shared-memory slab (the pipeline stages are free once
+    // tmem_full fires), then each takes 8 rows with lane <-> 4 consecutive channels: every global access
+    // of the functor is a contiguous warp transaction, and the transcendental-heavy gating runs on 16
+    // warps instead of 4.
+    constexpr int LPR = Epi::kPair ? BN / 8 : BN / 4;     // lanes per row
+    constexpr int RPI = 32 / LPR;                         // rows per iteration
+    constexpr int NIT = 8 / RPI;                          // iterations for this warp's 8 rows
+    constexpr int CW = BN / 4;                            // columns staged by this warp
+    const int q = warp & 3;                      // TMEM lane quarter = rows 32q .. 32q+31 of the tile
+    const int cg = warp >> 2;                    // column group staged by this warp; also its row octet
+    const int lc = lane % LPR, rsub = lane / LPR;
+    const int ncol = Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * lc : n0 + 4 * lc;   // this lane's 4 channels
+    const bool col_ok = Epi::kPair ? true : (ncol < N);
+    const int row0 = q * 32 + cg * 8;            // first of this warp's 8 rows (tile-relative)
+    // While the MMAs run: pull the rows this warp's epilogue will read into L2 (one request per 128-B line)
+    if (col_ok && (lc & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int p = m0 + row0 + i * RPI + rsub;
+        if (p < T) Epi::l2_prefetch(ep, b, p, ncol);
+      }
+    }
+    EpiCol cc{};
+    if (col_ok) cc = Epi::col(ep, ncol);
+    if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
+    mbar_wait(tmem_full_bar, 0);
+    if (warp == 4) TL_MARK(4);             // accumulator ready
+    tc_fence_after();
+    constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
+    float* slab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)q * 32 * STG_LD;
+    {
+      float v[CW];
+      tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW), v);
+      if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
+        float v2[CW];
+        tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cg * CW), v2);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] += v2[j];
+      }
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j)
+        *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
+    if (warp == 4) TL_MARK(5);             // staged to smem
+    const float* stg = slab + (size_t)(cg * 8) * STG_LD;
+    EpiPre pre[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int p = m0 + row0 + i * RPI + rsub;
+      if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int r = i * RPI + rsub;
+      const int p = m0 + row0 + r;
+      if constexpr (Epi::kPair) {
+        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
+        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + BN / 2 + 4 * lc);
+        if (p < T) {
+          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+          const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+          Epi::apply_pair(ep, b, p, ncol, gg, ff, cc, pre[i]);
+        }
+      } else {
+        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
+        if (p < T && col_ok) {
+          const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
+          Epi::apply(ep, b, p, ncol, vv, cc, pre[i]);
+        }
+      }
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------
 template <class Epi, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -198,7 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -238,132 +336,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      const uint32_t tx_bytes = three ? Cfg::STAGE : Cfg::STAGE / 2;
-      const int pre = total < STAGES ? total : STAGES;
+    // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+    const uint32_t tx_bytes = three ? Cfg::STAGE : Cfg::STAGE / 2;
+    const int pre = total < STAGES ? total : STAGES;
+    if (elect_one_sync()) {
       for (int it = 0; it < pre; ++it) {        // stages are initially free: no empty-wait needed
         mbar_expect_tx(full_bar(it), tx_bytes);
         load_b(it, it);
       }
-      pdl_wait();                               // activations below were written by the previous kernel
+    }
+    __syncwarp();
+    pdl_wait();                                 // activations below were written by the previous kernel
+    if (elect_one_sync()) {
       for (int it = 0; it < pre; ++it) load_a(it, it);
-      for (int it = pre; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    }
+    __syncwarp();
+    for (int it = pre; it < total; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (elect_one_sync()) {
         mbar_expect_tx(full_bar(s), tx_bytes);
         load_a(it, s);
         load_b(it, s);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        if (it == 0) TL_MARK(1);            // first operands landed
-        tc_fence_after();
+    // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+    const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+    const uint32_t idesc2 = umma_idesc_f16(TC_BM, 2 * BN);   // [wh ; wl] concatenated along N
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      if (it == 0) TL_MARK(1);            // first operands landed
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint64_t ah = umma_desc_sw128(tile_a(s, 0)), al = umma_desc_sw128(tile_a(s, 1));
-        const uint64_t bh = umma_desc_sw128(tile_b(s, 0)), bl = umma_desc_sw128(tile_b(s, 1));
+        const uint64_t bh = umma_desc_sw128(tile_b(s, 0));
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
           const uint64_t koff = (uint64_t)((k4 * 32) >> 4);   // +32 B per K=16 step inside the swizzled row
-          umma_f16(tmem_base, ah + koff, bh + koff, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+          const uint32_t acc = (it > 0 || k4 > 0) ? 1u : 0u;
           if (three) {
+            // xh*[wh;wl] as ONE N=2*BN MMA (the lo weight tile follows the hi tile in smem) into
+            // columns [0,BN) | [BN,2BN), then xl*wh into [0,BN): 2 operand-A reads per K-step, not 3
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc2, acc);
             umma_f16(tmem_base, al + koff, bh + koff, idesc, 1u);
-            umma_f16(tmem_base, ah + koff, bl + koff, idesc, 1u);
+          } else {
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
           }
         }
         umma_commit(empty_bar(s));          // frees the smem stage once these MMAs have read it
+        if (it == total - 1) umma_commit(tmem_full_bar);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);           // accumulator complete
-      TL_MARK(2);                           // all MMAs issued
+      __syncwarp();
     }
-    __syncwarp();
+    TL_MARK(2);                             // all MMAs issued
   }
   pdl_wait();   // every thread: the epilogue reads tensors the previous kernel wrote
-  {
-    // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
-    // tcgen05.ld hands each thread one accumulator ROW (a frame); a warp may only touch the TMEM lane
-    // quarter (warp % 4).  Global tensors are channels-last, so the four warps of a quarter stage their
-    // 32 x BN/4 blocks into one [32 rows][BN cols] shared-memory slab (the pipeline stages are free once
-    // tmem_full fires), then each takes 8 rows with lane <-> 4 consecutive channels: every global access
-    // of the functor is a contiguous warp transaction, and the transcendental-heavy gating runs on 16
-    // warps instead of 4.
-    constexpr int LPR = Epi::kPair ? BN / 8 : BN / 4;     // lanes per row
-    constexpr int RPI = 32 / LPR;                         // rows per iteration
-    constexpr int NIT = 8 / RPI;                          // iterations for this warp's 8 rows
-    constexpr int CW = BN / 4;                            // columns staged by this warp
-    const int q = warp & 3;                      // TMEM lane quarter = rows 32q .. 32q+31 of the tile
-    const int cg = warp >> 2;                    // column group staged by this warp; also its row octet
-    const int lc = lane % LPR, rsub = lane / LPR;
-    const int ncol = Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * lc : n0 + 4 * lc;   // this lane's 4 channels
-    const bool col_ok = Epi::kPair ? true : (ncol < N);
-    const int row0 = q * 32 + cg * 8;            // first of this warp's 8 rows (tile-relative)
-    // While the MMAs run: pull the rows this warp's epilogue will read into L2 (one request per 128-B line)
-    if (col_ok && (lc & 7) == 0) {
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int p = m0 + row0 + i * RPI + rsub;
-        if (p < T) Epi::l2_prefetch(ep, b, p, ncol);
-      }
-    }
-    EpiCol cc{};
-    if (col_ok) cc = Epi::col(ep, ncol);
-    if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
-    mbar_wait(tmem_full_bar, 0);
-    if (warp == 4) TL_MARK(4);             // accumulator ready
-    tc_fence_after();
-    constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
-    float* slab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)q * 32 * STG_LD;
-    {
-      float v[CW];
-      tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW), v);
-#pragma unroll
-      for (int j = 0; j < CW / 4; ++j)
-        *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
-    if (warp == 4) TL_MARK(5);             // staged to smem
-    const float* stg = slab + (size_t)(cg * 8) * STG_LD;
-    EpiPre pre[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int p = m0 + row0 + i * RPI + rsub;
-      if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
-    }
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int r = i * RPI + rsub;
-      const int p = m0 + row0 + r;
-      if constexpr (Epi::kPair) {
-        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
-        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + BN / 2 + 4 * lc);
-        if (p < T) {
-          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-          const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
-          Epi::apply_pair(ep, b, p, ncol, gg, ff, cc, pre[i]);
-        }
-      } else {
-        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
-        if (p < T && col_ok) {
-          const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
-          Epi::apply(ep, b, p, ncol, vv, cc, pre[i]);
-        }
-      }
-    }
-  }
+#ifdef DSVC_TIMELINE
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three, tl0);
+#else
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three);
+#endif
   if (warp == 4) TL_MARK(6);               // epilogue done
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 #endif
 }
