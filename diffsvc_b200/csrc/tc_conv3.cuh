@@ -15,7 +15,8 @@
 // operand-A read of each tcgen05.mma, ~64-72 cycles per instruction, not by L2->SM bytes), so it is
 // opt-in (DSVC_CONV_HALO=1) and kept as a documented experiment.
 //
-// Two mbarrier rings: A (2 slots x 36 KB, one per K-block) and B (weight tiles, one per (K-block, tap)).
+// Two mbarrier rings with their own producer warps: A (3 slots x 36 KB, one per K-block, warp 3) and
+// B (weight tiles, one per (K-block, tap), warp 0).
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -25,12 +26,12 @@ constexpr int TC3_HALO = 8;
 constexpr int TC3_AROWS = TC_BM + 2 * TC3_HALO;          // 144 frames
 constexpr int TC3_A_TILE = TC3_AROWS * TC_BK * 2;        // 18 KB (18 swizzle atoms)
 constexpr int TC3_A_SLOT = 2 * TC3_A_TILE;               // hi + lo
-constexpr int TC3_NA = 2;
+constexpr int TC3_NA = 3;
 
 template <int BN> struct Tc3Cfg {
   static constexpr int B_TILE = BN * TC_BK * 2;
   static constexpr int B_SLOT = 2 * B_TILE;               // hi + lo
-  static constexpr int NB = (BN == 64) ? 7 : 4;
+  static constexpr int NB = (BN == 64) ? 5 : 3;
   static constexpr int SMEM = TC3_NA * TC3_A_SLOT + NB * B_SLOT + 1024 + 256;
 };
 
@@ -92,7 +93,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-  if (warp == 3) TL_MARK(0);
+  if (warp == 4) TL_MARK(0);
 
   // weight tile(s) of iteration it = kb*3 + tap into B slot s
   auto load_b = [&](int it, int s) {
@@ -120,39 +121,26 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+    // ===== weight-tile producer (B ring) =====
     const int preb = total < NB ? total : NB;
     if (elect_one_sync()) {
       for (int it = 0; it < preb; ++it) load_b(it, it);        // weights: no dependency on the previous kernel
     }
     __syncwarp();
-    pdl_wait();
-    const int prea = kblocks < TC3_NA ? kblocks : TC3_NA;
-    if (elect_one_sync()) {
-      for (int kb = 0; kb < prea; ++kb) load_a(kb, kb);
-    }
-    __syncwarp();
-    int nexta = prea;
     for (int it = preb; it < total; ++it) {
-      const int kb = it / 3;
-      if (nexta <= kb + 1 && nexta < kblocks) {                 // keep the A ring one K-block ahead
-        const int s = nexta % TC3_NA;
-        mbar_wait(a_empty(s), ((uint32_t)(nexta / TC3_NA) & 1u) ^ 1u);
-        if (elect_one_sync()) load_a(nexta, s);
-        __syncwarp();
-        ++nexta;
-      }
       const int s = it % NB;
       mbar_wait(b_empty(s), ((uint32_t)(it / NB) & 1u) ^ 1u);
       if (elect_one_sync()) load_b(it, s);
       __syncwarp();
     }
-    while (nexta < kblocks) {
-      const int s = nexta % TC3_NA;
-      mbar_wait(a_empty(s), ((uint32_t)(nexta / TC3_NA) & 1u) ^ 1u);
-      if (elect_one_sync()) load_a(nexta, s);
+  } else if (warp == 3) {
+    // ===== activation-tile producer (A ring), decoupled from the B ring =====
+    pdl_wait();                                                // the plane was written by the previous kernel
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int s = kb % TC3_NA;
+      if (kb >= TC3_NA) mbar_wait(a_empty(s), ((uint32_t)(kb / TC3_NA) & 1u) ^ 1u);
+      if (elect_one_sync()) load_a(kb, s);
       __syncwarp();
-      ++nexta;
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====

@@ -252,3 +252,73 @@ def test_errors_are_loud():
         _lib.check(_lib.load().dsvc_diffnet_eval(dn.handle(), None, 0, None, None))   # null args / not prepared
     with pytest.raises(ValueError):
         dn(torch.zeros(2, 1, 128, 8, device=DEV), torch.tensor([1, 2], device=DEV), torch.zeros(2, 256, 8, device=DEV))
+
+
+# ------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("math_mode", ["fp32", "tc3f16"])
+@pytest.mark.parametrize("T", [1, 7, 129])
+def test_tiny_and_odd_lengths(math_mode, T):
+    """Frame counts below one tile, not a multiple of anything, and one frame past a tile boundary."""
+    gd, sd = _full_model(math_mode)
+    cond, x0, noise = _inputs(1, T, 3, seed=31)
+    sched = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    ref = O.sample(sd, sched, cond, x0, 3, noise)
+    xf = gd.sample(x0.to(DEV), cond.to(DEV), 3, None, noise.to(DEV)).cpu()
+    assert (xf - ref).abs().max().item() <= 5e-5
+
+
+def test_zero_steps_and_empty_item():
+    gd, sd = _full_model("tc3f16")
+    cond, x0, noise = _inputs(2, 40, 2, seed=3)
+    # t_start = 0: the loop body never runs; x comes back unchanged (diffusion.py:276 with t=0)
+    same = gd.sample(x0.to(DEV), cond.to(DEV), 0, None, None).cpu()
+    assert torch.equal(same, x0)
+    # an item of length 0 next to a full one: the full item must equal its stand-alone result
+    both = gd.sample(x0.to(DEV), cond.to(DEV), 2, None, noise.to(DEV), lengths=[40, 0]).cpu()
+    one = gd.sample(x0[:1].to(DEV), cond[:1].to(DEV), 2, None, noise[:, :1].contiguous().to(DEV)).cpu()
+    assert torch.equal(both[:1], one)
+
+
+def test_plms_interval_not_dividing_t():
+    """reversed(range(0, t, interval)) when interval does not divide t (diffusion.py:272)."""
+    gd, sd = _full_model("fp32")
+    cond, x0, _ = _inputs(1, 48, 1, seed=13)
+    sched = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    ref = O.sample(sd, sched, cond, x0, 250, None, pndm_speedup=60)     # t = 240, 180, 120, 60, 0
+    xf = gd.sample(x0.to(DEV), cond.to(DEV), 250, 60).cpu()
+    rng = max(1.0, ref.abs().max().item())
+    assert (xf - ref).abs().max().item() / rng <= 1e-5
+
+
+def test_weights_reload_rebuilds_handle():
+    """load_state_dict after first use must not keep stale device weights (utils.load_ckpt after .cuda())."""
+    gd, sd = _full_model("fp32")
+    cond, x0, _ = _inputs(1, 32, 1)
+    t = torch.tensor([5], device=DEV)
+    a = gd.denoise_fn(x0.to(DEV), t, cond.to(DEV)).cpu()
+    sd2 = O.synth_diffnet_weights(seed=99)
+    gd.denoise_fn.load_state_dict(sd2)
+    b = gd.denoise_fn(x0.to(DEV), t, cond.to(DEV)).cpu()
+    ref = O.diffnet_forward(sd2, x0, torch.tensor([5]), cond)
+    assert (b - ref).abs().max().item() <= 2e-5 and (a - b).abs().max().item() > 1e-3
+
+
+def test_vocoder_checkpoint_file_roundtrip(tmp_path):
+    """NsfHifiGAN() the reference's way: hparams['vocoder_ckpt'] + sibling config.json + ['generator'] in
+    weight_g/weight_v form (modules/nsf_hifigan/models.py:14-30)."""
+    import json
+    from diffsvc_b200.vocoders.nsf_hifigan import NsfHifiGAN
+    z = np.load(os.path.join(GOLD, "nsf_small.npz"))
+    ckpt = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ckpt/")}
+    h = {k[2:]: z[k].tolist() for k in z.files if k.startswith("h/")}
+    h.update(resblock="1", n_fft=512, win_size=512, hop_size=16, fmin=40, fmax=8000)
+    (tmp_path / "config.json").write_text(json.dumps(h))
+    torch.save({"generator": ckpt}, tmp_path / "model")
+    _hp(vocoder_ckpt=str(tmp_path / "model"), audio_sample_rate=16000, audio_num_mel_bins=8, hop_size=16, fft_size=512,
+        win_size=512, fmin=40, fmax=8000)
+    voc = NsfHifiGAN()
+    assert voc.h.num_mels == 8 and voc.model.hop == 16
+    mel = torch.from_numpy(z["mel"]).transpose(1, 2) / 2.30259           # back to "log10" mel [B,T,M]
+    wav = voc.spec2wav_torch(mel.to(DEV), f0=torch.from_numpy(z["f0"]).to(DEV),
+                             rand_ini=torch.from_numpy(z["rand_ini"]), sine_noise=torch.from_numpy(z["sine_noise"])).cpu()
+    assert (wav - torch.from_numpy(z["wav"]).reshape(-1)).abs().max().item() <= 5e-5
