@@ -250,10 +250,16 @@ static int tc_build_maps(dsvc_diffnet* h) {
   auto gemm = [&](TcGemmMaps& g, const PlaneBuf& a, int K, const F16Pair& w, int rows) -> int {
     DSVC_TRY(tc_make_a_map(&g.a_hi, a.hi.as<__half>(), B, T, K));
     DSVC_TRY(tc_make_a_map(&g.a_lo, a.lo.as<__half>(), B, T, K));
+    DSVC_TRY(tc_make_a_map(&g.a64_hi, a.hi.as<__half>(), B, T, K, 64));
+    DSVC_TRY(tc_make_a_map(&g.a64_lo, a.lo.as<__half>(), B, T, K, 64));
+    DSVC_TRY(tc_make_a_map(&g.a32_hi, a.hi.as<__half>(), B, T, K, 32));
+    DSVC_TRY(tc_make_a_map(&g.a32_lo, a.lo.as<__half>(), B, T, K, 32));
     DSVC_TRY(tc_make_b_map(&g.b_hi, w.hi.as<__half>(), rows, K, 128));
     DSVC_TRY(tc_make_b_map(&g.b_lo, w.lo.as<__half>(), rows, K, 128));
     DSVC_TRY(tc_make_b_map(&g.b32_hi, w.hi.as<__half>(), rows, K, 32));
     DSVC_TRY(tc_make_b_map(&g.b32_lo, w.lo.as<__half>(), rows, K, 32));
+    DSVC_TRY(tc_make_b_map(&g.b64_hi, w.hi.as<__half>(), rows, K, 64));
+    DSVC_TRY(tc_make_b_map(&g.b64_lo, w.lo.as<__half>(), rows, K, 64));
     return DSVC_OK;
   };
   DSVC_TRY(gemm(h->maps.in, h->XIN, M, h->h_in, C));
@@ -301,7 +307,7 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
   const bool tc = h->tc;
   const int dil = 1 << (l % h->cfg.dilation_cycle_length);
   EpiGate::Params e{};
-  e.CP = h->CP.as<float>() + (size_t)l * B * T * 2 * C; e.Z = h->Z.view(tc); e.Tmax = T; e.C = C;
+  e.CP = h->CP.as<float>() + (size_t)l * B * T * 2 * C; e.Z = h->Z.view(tc); e.Tmax = T; e.C = C; e.fast = tc ? 1 : 0;
   if (tc) {
     e.wscale = h->h_dil[l]->inv_scale;
     const TcGemmMaps& m = h->maps.dil[l];
@@ -325,7 +331,7 @@ static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
   e.bias = h->b_out.as<float>() + (size_t)l * 2 * C; e.dtab = h->dtab.as<float>(); e.st = h->state.as<StepState>();
   e.lengths = h->lengths.as<int>();
   e.X = h->X.as<float>(); e.S = h->S.as<float>(); e.Y = h->Y.view(tc); e.SP = h->SP.view(tc);
-  e.Tmax = T; e.C = C; e.L = L; e.layer = l; e.tsel = tsel;
+  e.Tmax = T; e.C = C; e.L = L; e.layer = l; e.tsel = tsel; e.fast = tc ? 1 : 0;
   if (tc) {
     e.wscale = h->h_out[l]->inv_scale;
     return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s);

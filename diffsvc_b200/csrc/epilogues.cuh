@@ -47,12 +47,27 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 __device__ __forceinline__ void plane_store4(const Plane& pl, size_t idx, const float (&v)[4]) {
   if (pl.f32) *reinterpret_cast<float4*>(pl.f32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
   if (pl.hi) {
-    __half h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_f16(v[i], h[i], l[i]);
-    *reinterpret_cast<uint2*>(pl.hi + idx) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(pl.lo + idx) = *reinterpret_cast<uint2*>(l);
+    // packed conversions: hi = rn_f16(v), lo = rn_f16(v - hi), two elements per instruction
+    const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+    uint2 hp, lp;
+    hp.x = *reinterpret_cast<const uint32_t*>(&h01); hp.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lp.x = *reinterpret_cast<const uint32_t*>(&l01); lp.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(pl.hi + idx) = hp;
+    *reinterpret_cast<uint2*>(pl.lo + idx) = lp;
   }
+}
+
+// sigmoid(g) * tanh(f) from two ex2.approx and two rcp.approx:  1/(1+e^-g) * (1 - 2/(1+e^2f)).
+// Absolute error ~1e-7 on a value in (-1, 1) -- what matters for an operand of the next contraction;
+// used by the tensor-core path only (its own arithmetic error is ~1e-6), the FFMA path keeps expf/tanhf.
+__device__ __forceinline__ float gate_fast(float g, float f) {
+  const float eg = __expf(-g);
+  const float ef = __expf(2.0f * f);
+  const float sg = __fdividef(1.0f, 1.0f + eg);
+  const float th = 1.0f - __fdividef(2.0f, 1.0f + ef);      // ef = inf -> 1, ef = 0 -> -1
+  return sg * th;
 }
 
 // ---- input_projection + ReLU (net.py:121,123), and the conv-input plane of layer 0 ----------
@@ -122,6 +137,7 @@ struct EpiGate {
     Plane Z;             // [B][Tmax][C]
     int Tmax, C;
     float wscale;
+    int fast;            // tensor-core path: gate_fast()
   };
   __device__ static __forceinline__ EpiCol col(const Params&, int) { return EpiCol{}; }
   __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int c0) {
@@ -141,8 +157,13 @@ struct EpiGate {
     const float gg[4] = {g[0] * e.wscale + r.a.x, g[1] * e.wscale + r.a.y, g[2] * e.wscale + r.a.z, g[3] * e.wscale + r.a.w};
     const float ff[4] = {f[0] * e.wscale + r.b.x, f[1] * e.wscale + r.b.y, f[2] * e.wscale + r.b.z, f[3] * e.wscale + r.b.w};
     float z[4];
+    if (e.fast) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) z[i] = sigmoidf_(gg[i]) * tanhf(ff[i]);
+      for (int i = 0; i < 4; ++i) z[i] = gate_fast(gg[i], ff[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = sigmoidf_(gg[i]) * tanhf(ff[i]);
+    }
     plane_store4(e.Z, ((size_t)b * e.Tmax + p) * e.C + c0, z);
   }
 };
@@ -163,6 +184,7 @@ struct EpiOutProj {
     int Tmax, C, L, layer;
     int tsel;
     float wscale;
+    int fast;                // tensor-core path: (x + r) * (1/sqrt 2) instead of the IEEE division
   };
   __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
     EpiCol c;
@@ -193,9 +215,14 @@ struct EpiOutProj {
     const float v[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     if (n < e.C) {
       const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
-      const float s2 = 1.41421356237309504880f;
-      float x[4] = {div_rn(add_rn(r.a.x, v[0]), s2), div_rn(add_rn(r.a.y, v[1]), s2),
-                    div_rn(add_rn(r.a.z, v[2]), s2), div_rn(add_rn(r.a.w, v[3]), s2)};
+      const float s2 = 1.41421356237309504880f, is2 = 0.70710678118654752440f;
+      float x[4];
+      if (e.fast) {
+        x[0] = (r.a.x + v[0]) * is2; x[1] = (r.a.y + v[1]) * is2; x[2] = (r.a.z + v[2]) * is2; x[3] = (r.a.w + v[3]) * is2;
+      } else {
+        x[0] = div_rn(add_rn(r.a.x, v[0]), s2); x[1] = div_rn(add_rn(r.a.y, v[1]), s2);
+        x[2] = div_rn(add_rn(r.a.z, v[2]), s2); x[3] = div_rn(add_rn(r.a.w, v[3]), s2);
+      }
       *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
       if (e.layer + 1 < e.L) {
         const bool live = p < e.lengths[b];

@@ -35,7 +35,10 @@ struct TcGemmMaps {
   CUtensorMap a_hi, a_lo;        // activation planes, box {64 ch, 128 frames, 1 item}
   CUtensorMap b_hi, b_lo;        // weights, box {64, 128 rows}   (BN = 128 tiles)
   CUtensorMap b32_hi, b32_lo;    // weights, box {64, 32 rows}    (BN = 64 tiles: two boxes per stage)
+  CUtensorMap b64_hi, b64_lo;    // weights, box {64, 64 rows}    (BN = 256 gate|filter tiles: four boxes per stage)
   CUtensorMap a144_hi, a144_lo;  // dilated-conv layers only: box {64 ch, 144 frames} (tc_conv3.cuh)
+  CUtensorMap a64_hi, a64_lo;    // activation slices for cluster multicast: box {64 ch, 64 frames} (CS = 2)
+  CUtensorMap a32_hi, a32_lo;    //                                           box {64 ch, 32 frames} (CS = 4)
 };
 struct TcMaps {
   TcGemmMaps in, skip, head;
@@ -50,7 +53,7 @@ constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB: one [128 rows][64 fp16]
 template <int BN> struct TcCfg {
   static constexpr int B_TILE = BN * TC_BK * 2;
   static constexpr int STAGE = 2 * (TC_A_TILE + B_TILE);     // A_hi, A_lo, B_hi, B_lo
-  static constexpr int STAGES = (BN == 64) ? 4 : 3;           // 192 KB of operands in flight either way
+  static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);   // 192 KB of operands in flight
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 128 /*barriers*/;
 };
 
@@ -88,6 +91,25 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// multicast variants: the tile (and its complete_tx) lands at the same smem offset in every CTA of the mask
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -179,26 +201,36 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
     // tmem_full fires), then each takes 8 rows with lane <-> 4 consecutive channels: every global access
     // of the functor is a contiguous warp transaction, and the transcendental-heavy gating runs on 16
     // warps instead of 4.
-    constexpr int LPR = Epi::kPair ? BN / 8 : BN / 4;     // lanes per row
+    constexpr int NCH = Epi::kPair ? BN / 8 : BN / 4;     // float4 chunks per row (pair: gate chunks)
+    constexpr int NH = NCH > 32 ? NCH / 32 : 1;           // column passes (BN = 256 plain tiles: 2)
+    constexpr int LPR = NCH / NH;                         // lanes per row
     constexpr int RPI = 32 / LPR;                         // rows per iteration
     constexpr int NIT = 8 / RPI;                          // iterations for this warp's 8 rows
     constexpr int CW = BN / 4;                            // columns staged by this warp
     const int q = warp & 3;                      // TMEM lane quarter = rows 32q .. 32q+31 of the tile
     const int cg = warp >> 2;                    // column group staged by this warp; also its row octet
     const int lc = lane % LPR, rsub = lane / LPR;
-    const int ncol = Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * lc : n0 + 4 * lc;   // this lane's 4 channels
-    const bool col_ok = Epi::kPair ? true : (ncol < N);
     const int row0 = q * 32 + cg * 8;            // first of this warp's 8 rows (tile-relative)
+    auto col_of = [&](int h) {                   // this lane's 4 channels in column pass h
+      const int ch = lc + h * LPR;
+      return Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * ch : n0 + 4 * ch;
+    };
     // While the MMAs run: pull the rows this warp's epilogue will read into L2 (one request per 128-B line)
-    if (col_ok && (lc & 7) == 0) {
+    EpiCol cc[NH];
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int p = m0 + row0 + i * RPI + rsub;
-        if (p < T) Epi::l2_prefetch(ep, b, p, ncol);
+    for (int h = 0; h < NH; ++h) {
+      const int ncol = col_of(h);
+      const bool col_ok = Epi::kPair ? true : (ncol < N);
+      if (col_ok && (lc & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int p = m0 + row0 + i * RPI + rsub;
+          if (p < T) Epi::l2_prefetch(ep, b, p, ncol);
+        }
       }
+      cc[h] = EpiCol{};
+      if (col_ok) cc[h] = Epi::col(ep, ncol);
     }
-    EpiCol cc{};
-    if (col_ok) cc = Epi::col(ep, ncol);
     if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
     mbar_wait(tmem_full_bar, 0);
     if (warp == 4) TL_MARK(4);             // accumulator ready
@@ -206,51 +238,66 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
     constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
     float* slab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)q * 32 * STG_LD;
     {
-      float v[CW];
-      tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW), v);
-      if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
-        float v2[CW];
-        tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cg * CW), v2);
+      constexpr int LW = CW > 32 ? 32 : CW;      // columns per tcgen05.ld
 #pragma unroll
-        for (int j = 0; j < CW; ++j) v[j] += v2[j];
+      for (int c0 = 0; c0 < CW; c0 += LW) {
+        float v[LW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW + c0);
+        tmem_ld_cols<LW>(taddr, v);
+        if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
+          float v2[LW];
+          tmem_ld_cols<LW>(taddr + (uint32_t)BN, v2);
+#pragma unroll
+          for (int j = 0; j < LW; ++j) v[j] += v2[j];
+        }
+#pragma unroll
+        for (int j = 0; j < LW / 4; ++j)
+          *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + c0 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-#pragma unroll
-      for (int j = 0; j < CW / 4; ++j)
-        *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
     if (warp == 4) TL_MARK(5);             // staged to smem
     const float* stg = slab + (size_t)(cg * 8) * STG_LD;
-    EpiPre pre[NIT];
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int p = m0 + row0 + i * RPI + rsub;
-      if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
-    }
+    for (int h = 0; h < NH; ++h) {
+      const int ncol = col_of(h);
+      const bool col_ok = Epi::kPair ? true : (ncol < N);
+      const int ch = lc + h * LPR;
+      EpiPre pre[NIT];
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int r = i * RPI + rsub;
-      const int p = m0 + row0 + r;
-      if constexpr (Epi::kPair) {
-        const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
-        const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + BN / 2 + 4 * lc);
-        if (p < T) {
-          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-          const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
-          Epi::apply_pair(ep, b, p, ncol, gg, ff, cc, pre[i]);
-        }
-      } else {
-        const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * lc);
-        if (p < T && col_ok) {
-          const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
-          Epi::apply(ep, b, p, ncol, vv, cc, pre[i]);
+      for (int i = 0; i < NIT; ++i) {
+        const int p = m0 + row0 + i * RPI + rsub;
+        if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int r = i * RPI + rsub;
+        const int p = m0 + row0 + r;
+        if constexpr (Epi::kPair) {
+          const float4 gv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * ch);
+          const float4 fv = *reinterpret_cast<const float4*>(stg + r * STG_LD + BN / 2 + 4 * ch);
+          if (p < T) {
+            const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+            Epi::apply_pair(ep, b, p, ncol, gg, ff, cc[h], pre[i]);
+          }
+        } else {
+          const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * ch);
+          if (p < T && col_ok) {
+            const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
+            Epi::apply(ep, b, p, ncol, vv, cc[h], pre[i]);
+          }
         }
       }
     }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <class Epi, int BN>
+// CS = thread-block-cluster size along the channel-tile axis.  The CS CTAs of a cluster compute the same
+// 128 frames for different channel tiles, so each loads 1/CS of the activation tile and multicasts it
+// to its peers: L2 -> SM activation traffic per CTA drops by CS (the mainloop is bound by operand
+// delivery, ~64 B/clk/SM and ~6.3 KB/clk chip-wide).
+template <class Epi, int BN, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -290,7 +337,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CS);            // every CTA of the cluster must have drained the stage
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -301,10 +348,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   if (warp == 3) TL_MARK(0);   // setup done
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
   // weight tile(s) of pipeline iteration `it` into stage s (weights are constants: no dependency on
   // the previous kernel, so the first STAGES of them are requested before griddepcontrol.wait)
@@ -314,6 +364,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if constexpr (BN == 128) {
       tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0), kb * TC_BK, row);
       if (three) tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1), kb * TC_BK, row);
+    } else if constexpr (BN == 256) {
+      if constexpr (Epi::kPair) {
+        // [128 gate | 128 filter] from two packed super-tiles [64 gate | 64 filter]: four 64-row boxes
+        const int sb = tap * N + (int)blockIdx.y * 256;
+        for (int lo = 0; lo < (three ? 2 : 1); ++lo) {
+          const CUtensorMap* mp = lo ? &tmBl : &tmBh;
+          tma_load_2d(mp, full_bar(s), tile_b(s, lo), kb * TC_BK, sb);                        // gate, super-tile 0
+          tma_load_2d(mp, full_bar(s), tile_b(s, lo) + 64u * 128u, kb * TC_BK, sb + 128);     // gate, super-tile 1
+          tma_load_2d(mp, full_bar(s), tile_b(s, lo) + 128u * 128u, kb * TC_BK, sb + 64);     // filter, super-tile 0
+          tma_load_2d(mp, full_bar(s), tile_b(s, lo) + 192u * 128u, kb * TC_BK, sb + 192);    // filter, super-tile 1
+        }
+      } else {
+        tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0), kb * TC_BK, row);
+        tma_load_2d(&tmBh, full_bar(s), tile_b(s, 0) + 128u * 128u, kb * TC_BK, row + 128);
+        if (three) {
+          tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1), kb * TC_BK, row);
+          tma_load_2d(&tmBl, full_bar(s), tile_b(s, 1) + 128u * 128u, kb * TC_BK, row + 128);
+        }
+      }
     } else {
       // two 32-row boxes.  Pair (gate|filter) tiles live in a 128-row super-tile packed as
       // [64 gate rows | 64 filter rows]: tile h of super-tile j takes gate rows 128j+32h and
@@ -331,8 +400,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   auto load_a = [&](int it, int s) {
     const int tap = it / kblocks, kb = it - tap * kblocks;
     const int frame = m0 + (taps == 3 ? (tap - 1) * dil : 0);
-    tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
-    if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
+    if constexpr (CS == 1) {
+      tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
+      if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
+    } else {
+      // this CTA's slice of the tile (TC_BM/CS frames), delivered to all CS CTAs
+      constexpr int SL = TC_BM / CS;
+      const uint32_t off = crank * (uint32_t)(SL * TC_BK * 2);
+      tma_load_3d_mc(&tmAh, full_bar(s), tile_a(s, 0) + off, kb * TC_BK, frame + (int)crank * SL, b, cmask);
+      if (three) tma_load_3d_mc(&tmAl, full_bar(s), tile_a(s, 1) + off, kb * TC_BK, frame + (int)crank * SL, b, cmask);
+    }
   };
 
   if (warp == 0) {
@@ -365,7 +442,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
     const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
-    const uint32_t idesc2 = umma_idesc_f16(TC_BM, 2 * BN);   // [wh ; wl] concatenated along N
+    const uint32_t idesc2 = umma_idesc_f16(TC_BM, BN == 256 ? 256 : 2 * BN);   // [wh ; wl] concatenated along N
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -379,7 +456,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
           const uint64_t koff = (uint64_t)((k4 * 32) >> 4);   // +32 B per K=16 step inside the swizzled row
           const uint32_t acc = (it > 0 || k4 > 0) ? 1u : 0u;
-          if (three) {
+          if (three && BN == 256) {
+            // N = 2*BN would exceed the 256-column MMA limit: three N=256 MMAs, xh*wl in its own accumulator
+            const uint64_t bl = umma_desc_sw128(tile_b(s, 1));
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
+            umma_f16(tmem_base + (uint32_t)BN, ah + koff, bl + koff, idesc, acc);
+            umma_f16(tmem_base, al + koff, bh + koff, idesc, 1u);
+          } else if (three) {
             // xh*[wh;wl] as ONE N=2*BN MMA (the lo weight tile follows the hi tile in smem) into
             // columns [0,BN) | [BN,2BN), then xl*wh into [0,BN): 2 operand-A reads per K-step, not 3
             umma_f16(tmem_base, ah + koff, bh + koff, idesc2, acc);
@@ -388,7 +471,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
           }
         }
-        umma_commit(empty_bar(s));          // frees the smem stage once these MMAs have read it
+        // frees the smem stage once these MMAs have read it (in every CTA of the cluster: peers multicast into it)
+        if constexpr (CS == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
         if (it == total - 1) umma_commit(tmem_full_bar);   // accumulator complete
       }
       __syncwarp();
@@ -404,6 +488,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 4) TL_MARK(6);               // epilogue done
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
@@ -433,12 +518,12 @@ static inline int tc_encode_fn(PFN_encodeTiled* out) {
 }
 
 // activation plane [B][T][K] fp16, box = {64 channels, 128 frames, 1 item}
-static inline int tc_make_a_map(CUtensorMap* m, const __half* base, int B, int T, int K) {
+static inline int tc_make_a_map(CUtensorMap* m, const __half* base, int B, int T, int K, int box_rows = TC_BM) {
   PFN_encodeTiled enc;
   DSVC_TRY(tc_encode_fn(&enc));
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)T * K * 2};
-  cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+  cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -465,11 +550,17 @@ inline bool tc_use_pdl() {
   return v == 1;
 }
 
-template <class Epi, int BN>
-int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
+inline int tc_cluster_pref() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("DSVC_TC_CLUSTER"); v = e ? atoi(e) : -1; }
+  return v;   // -1 = automatic, 1 = off, 2 / 4 = forced upper bound
+}
+
+template <class Epi, int BN, int CS>
+int tc_launch_cs(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
                  cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = tc_gemm_kernel<Epi, BN>;
+  auto kern = tc_gemm_kernel<Epi, BN, CS>;
   if (!attr_set) {
     DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     attr_set = true;
@@ -479,16 +570,44 @@ int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int 
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (tc_use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = CS;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = tc_use_pdl() ? 1 : 0;
-  const CUtensorMap& bh = (BN == 128) ? m.b_hi : m.b32_hi;
-  const CUtensorMap& bl = (BN == 128) ? m.b_lo : m.b32_lo;
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, passes));
+  cfg.numAttrs = na;
+  const bool b64 = (BN == 256) && Epi::kPair;
+  const CUtensorMap& bh = (BN == 64) ? m.b32_hi : (b64 ? m.b64_hi : m.b_hi);
+  const CUtensorMap& bl = (BN == 64) ? m.b32_lo : (b64 ? m.b64_lo : m.b_lo);
+  const CUtensorMap& ah = (CS == 1) ? m.a_hi : (CS == 2 ? m.a64_hi : m.a32_hi);
+  const CUtensorMap& al = (CS == 1) ? m.a_lo : (CS == 2 ? m.a64_lo : m.a32_lo);
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, e, T, K, N, taps, dil, passes));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
+}
+
+template <class Epi, int BN>
+int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
+                 cudaStream_t s) {
+  const int ntiles = ceil_div(N, BN);
+  // Cluster multicast of the activation tile is correct but measured neutral-to-slower: the mainloop is bound
+  // by shared-memory bandwidth (TMA fill + UMMA operand reads ~ 128 B/clk/SM), which multicast does not
+  // reduce.  Opt-in via DSVC_TC_CLUSTER=2|4.
+  const int pref = tc_cluster_pref();
+  const int cap = (pref < 0 || BN == 256) ? 1 : pref;
+  if (cap >= 4 && ntiles % 4 == 0) return tc_launch_cs<Epi, BN, 4>(m, e, B, T, K, N, taps, dil, passes, s);
+  if (cap >= 2 && ntiles % 2 == 0) return tc_launch_cs<Epi, BN, 2>(m, e, B, T, K, N, taps, dil, passes, s);
+  return tc_launch_cs<Epi, BN, 1>(m, e, B, T, K, N, taps, dil, passes, s);
 }
 
 // 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
@@ -501,11 +620,22 @@ inline bool tc_narrow_tiles(int B, int T, int N) {
   return (long long)ceil_div(T, TC_BM) * ceil_div(N, 128) * B < 148;
 }
 
+// 256-wide tiles (best operand reuse: ~235 vs 281 smem bytes per column per K-step) once they fill the GPU
+inline bool tc_wide_tiles(int B, int T, int N) {
+  static int forced = -2;
+  if (forced == -2) { const char* e = getenv("DSVC_TC_BN"); forced = e ? atoi(e) : -1; }
+  if (N % 256 != 0) return false;
+  if (forced == 256) return true;
+  if (forced == 64 || forced == 128) return false;
+  return (long long)ceil_div(T, TC_BM) * (N / 256) * B >= 120;
+}
+
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
               cudaStream_t s) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
   if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s);
+  if (tc_wide_tiles(B, T, N)) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s);
   return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s);
 }
 
