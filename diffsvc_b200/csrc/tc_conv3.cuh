@@ -184,9 +184,9 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   }
   pdl_wait();
 #ifdef DSVC_TIMELINE
-  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three, tl0);
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three, tl0);
 #else
-  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three);
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three);
 #endif
   if (warp == 4) TL_MARK(6);
   tc_fence_before();

@@ -188,8 +188,8 @@ __device__ long long g_timeline[1024][8];
 // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
 template <class Epi, int BN>
 __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint8_t* smem_raw, uint32_t smem_base,
-                                            uint32_t tmem_base, uint32_t tmem_full_bar, int T, int N, int m0, int n0,
-                                            int b, int warp, int lane, bool two_acc
+                                            uint32_t tmem_base, uint32_t tmem_full_bar, uint32_t tmem_parity, int T, int N,
+                                            int m0, int ny, int b, int warp, int lane, bool two_acc
 #ifdef DSVC_TIMELINE
                                             , long long tl0
 #endif
@@ -213,7 +213,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
     const int row0 = q * 32 + cg * 8;            // first of this warp's 8 rows (tile-relative)
     auto col_of = [&](int h) {                   // this lane's 4 channels in column pass h
       const int ch = lc + h * LPR;
-      return Epi::kPair ? (int)blockIdx.y * (BN / 2) + 4 * ch : n0 + 4 * ch;
+      return Epi::kPair ? ny * (BN / 2) + 4 * ch : ny * BN + 4 * ch;
     };
     // While the MMAs run: pull the rows this warp's epilogue will read into L2 (one request per 128-B line)
     EpiCol cc[NH];
@@ -232,7 +232,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       if (col_ok) cc[h] = Epi::col(ep, ncol);
     }
     if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, tmem_parity);
     if (warp == 4) TL_MARK(4);             // accumulator ready
     tc_fence_after();
     constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
@@ -481,9 +481,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   pdl_wait();   // every thread: the epilogue reads tensors the previous kernel wrote
 #ifdef DSVC_TIMELINE
-  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three, tl0);
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three, tl0);
 #else
-  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, T, N, m0, n0, b, warp, lane, three);
+  tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three);
 #endif
   if (warp == 4) TL_MARK(6);               // epilogue done
   tc_fence_before();
