@@ -10,5 +10,6 @@ from .net import DiffNet  # noqa: F401
 from .diffusion import GaussianDiffusion, OfflineGaussianDiffusion  # noqa: F401
 from .vocoders.base_vocoder import VOCODERS, BaseVocoder, get_vocoder_cls, register_vocoder  # noqa: F401
 from .vocoders.nsf_hifigan import NsfHifiGAN  # noqa: F401
+from .vocoders.hifigan import HifiGAN, HifiGanGenerator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -71,7 +71,8 @@ class NsfConfig(C.Structure):
                 ("num_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * MAX_STAGES),
                 ("upsample_kernel_sizes", C.c_int32 * MAX_STAGES), ("num_kernels", C.c_int32),
                 ("resblock_kernel_sizes", C.c_int32 * MAX_KERNELS), ("num_dilations", C.c_int32),
-                ("resblock_dilation_sizes", (C.c_int32 * MAX_DILATIONS) * MAX_KERNELS), ("harmonic_num", C.c_int32)]
+                ("resblock_dilation_sizes", (C.c_int32 * MAX_DILATIONS) * MAX_KERNELS), ("harmonic_num", C.c_int32),
+                ("has_source", C.c_int32)]
 
 
 class NsfWeights(C.Structure):

@@ -320,8 +320,11 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
     ch >>= 1;
   }
   DSVC_REQUIRE(cfg->num_mels % 4 == 0 || true, "num_mels");
-  DSVC_TRY(h->lin_w.upload(w->source_linear_w, (size_t)dim * 4, s));
-  DSVC_TRY(h->lin_b.upload(w->source_linear_b, 4, s));
+  if (cfg->has_source) {
+    DSVC_REQUIRE(w->source_linear_w && w->source_linear_b && w->noise_convs_w && w->noise_convs_b, "has_source without source weights");
+    DSVC_TRY(h->lin_w.upload(w->source_linear_w, (size_t)dim * 4, s));
+    DSVC_TRY(h->lin_b.upload(w->source_linear_b, 4, s));
+  }
   DSVC_TRY(upload_conv(h->pre, w->conv_pre_w, w->conv_pre_b, cfg->upsample_initial_channel, cfg->num_mels, 7, s));
   ch = cfg->upsample_initial_channel;
   int rest = h->hop;
@@ -336,8 +339,10 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
     h->noise.emplace_back(new ConvW());
     const int Kn = (i + 1 < ns) ? 2 * rest : 1;
     h->noise[i]->Cin = 1; h->noise[i]->Cout = cout; h->noise[i]->K = Kn;
-    DSVC_TRY(h->noise[i]->w.upload(w->noise_convs_w[i], (size_t)cout * Kn * 4, s));
-    DSVC_TRY(h->noise[i]->b.upload(w->noise_convs_b[i], (size_t)cout * 4, s));
+    if (cfg->has_source) {
+      DSVC_TRY(h->noise[i]->w.upload(w->noise_convs_w[i], (size_t)cout * Kn * 4, s));
+      DSVC_TRY(h->noise[i]->b.upload(w->noise_convs_b[i], (size_t)cout * 4, s));
+    }
     for (int j = 0; j < nk; ++j)
       for (int m = 0; m < nd; ++m) {
         const int idx = (i * nk + j) * nd + m;
@@ -367,7 +372,8 @@ void dsvc_nsf_destroy(dsvc_nsf_t* h) { delete h; }
 
 int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const float* rand_ini, const float* sine_noise,
                      uint64_t seed, float mel_scale, float* wav, int32_t B, int32_t T, void* stream) {
-  DSVC_REQUIRE(h && mel && f0 && wav, "dsvc_nsf_forward: null argument");
+  DSVC_REQUIRE(h && mel && wav, "dsvc_nsf_forward: null argument");
+  DSVC_REQUIRE(!f0 || h->cfg.has_source, "dsvc_nsf_forward: f0 given but the generator was created without source weights");
   DSVC_REQUIRE(B > 0 && T > 0, "dsvc_nsf_forward: B and T must be positive");
   cudaStream_t s = (cudaStream_t)stream;
   const dsvc_nsf_config& cfg = h->cfg;
@@ -397,8 +403,8 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
   DSVC_TRY(h->bufR1.reserve(maxact * 4));
   DSVC_TRY(h->bufS.reserve(maxact * 4));
 
-  // ---- V0 harmonic source ----
-  {
+  // ---- V0 harmonic source (skipped without f0, like the reference's `if f0 is not None`) ----
+  if (f0) {
     SrcDims d{B, T, hop, dim, (float)cfg.sampling_rate};
     const int nseq = B * dim;
     src_frames1_kernel<<<ceil_div(nseq, 64), 64, 0, s>>>(d, f0, rand_ini, seed, h->S1.as<double>(), h->E.as<double>());
@@ -440,7 +446,7 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
       if (u == 1) { p.nphase = 1; p.in_off = p.tpad; }
       DSVC_TRY(launch_affine(p, e, s));
     }
-    {  // x = x + noise_convs[i](har_source)
+    if (f0) {  // x = x + noise_convs[i](har_source)
       const ConvW& nc = *h->noise[i];
       const int stride = (i + 1 < ns) ? rest : 1, pad = (i + 1 < ns) ? rest / 2 : 0;
       const size_t shbytes = (size_t)(31 * stride + nc.K) * 4;

@@ -14,6 +14,7 @@ Replaced modules -> ours:
     network.diff.diffusion         -> diffsvc_b200.diffusion  (GaussianDiffusion, OfflineGaussianDiffusion)
     network.vocoders.nsf_hifigan   -> diffsvc_b200.vocoders.nsf_hifigan (NsfHifiGAN, registered in the reference's VOCODERS)
     modules.nsf_hifigan.models     -> diffsvc_b200.vocoders.nsf_models  (load_model, Generator)
+    network.vocoders.hifigan       -> diffsvc_b200.vocoders.hifigan     (HifiGAN, load_model; 24 kHz models)
 """
 import importlib
 import importlib.abc
@@ -26,6 +27,7 @@ ALIASES = {
     "network.diff.diffusion": "diffsvc_b200.diffusion",
     "network.vocoders.nsf_hifigan": "diffsvc_b200.vocoders.nsf_hifigan",
     "modules.nsf_hifigan.models": "diffsvc_b200.vocoders.nsf_models",
+    "network.vocoders.hifigan": "diffsvc_b200.vocoders.hifigan",
 }
 
 

@@ -93,6 +93,8 @@ class Generator:
             cfg.upsample_rates[i] = int(h.upsample_rates[i])
             cfg.upsample_kernel_sizes[i] = int(h.upsample_kernel_sizes[i])
         cfg.num_kernels, cfg.num_dilations, cfg.harmonic_num = nk, nd, 8
+        self.has_source = "m_source.l_linear.weight" in sd
+        cfg.has_source = 1 if self.has_source else 0
         for j in range(nk):
             cfg.resblock_kernel_sizes[j] = int(h.resblock_kernel_sizes[j])
             assert len(h.resblock_dilation_sizes[j]) == nd
@@ -113,11 +115,12 @@ class Generator:
             return arr
 
         w = _lib.NsfWeights()
-        w.source_linear_w, w.source_linear_b = f("m_source.l_linear.weight"), f("m_source.l_linear.bias")
+        if self.has_source:
+            w.source_linear_w, w.source_linear_b = f("m_source.l_linear.weight"), f("m_source.l_linear.bias")
+            w.noise_convs_w = fa(["noise_convs.%d.weight" % i for i in range(ns)])
+            w.noise_convs_b = fa(["noise_convs.%d.bias" % i for i in range(ns)])
         w.conv_pre_w, w.conv_pre_b = f("conv_pre.weight"), f("conv_pre.bias")
         w.ups_w, w.ups_b = fa(["ups.%d.weight" % i for i in range(ns)]), fa(["ups.%d.bias" % i for i in range(ns)])
-        w.noise_convs_w = fa(["noise_convs.%d.weight" % i for i in range(ns)])
-        w.noise_convs_b = fa(["noise_convs.%d.bias" % i for i in range(ns)])
         idx = [(i * nk + j, m) for i in range(ns) for j in range(nk) for m in range(nd)]
         w.convs1_w = fa(["resblocks.%d.convs1.%d.weight" % im for im in idx])
         w.convs1_b = fa(["resblocks.%d.convs1.%d.bias" % im for im in idx])
@@ -134,9 +137,11 @@ class Generator:
         """mel [B, T, num_mels] channels-last (scaled by mel_scale on load), f0 [B, T] -> wav [B, T*hop]."""
         assert self._h is not None, "Generator has no weights loaded"
         mel = mel.detach().to(torch.float32).contiguous()
-        f0 = f0.detach().to(torch.float32).contiguous()
         B, T, M = mel.shape
-        assert M == self.h.num_mels and tuple(f0.shape) == (B, T), (mel.shape, f0.shape)
+        assert M == self.h.num_mels, (mel.shape, self.h.num_mels)
+        if f0 is not None:
+            f0 = f0.detach().to(mel.device, torch.float32).contiguous()
+            assert tuple(f0.shape) == (B, T), (mel.shape, f0.shape)
         wav = torch.empty(B, T * self.hop, device=mel.device, dtype=torch.float32)
         ri = sn = None
         if rand_ini is not None:
@@ -148,11 +153,11 @@ class Generator:
             sn = _lib.dptr(sine_noise)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        _lib.check(_lib.load().dsvc_nsf_forward(self._h, _lib.dptr(mel), _lib.dptr(f0), ri, sn, C.c_uint64(seed),
+        _lib.check(_lib.load().dsvc_nsf_forward(self._h, _lib.dptr(mel), None if f0 is None else _lib.dptr(f0), ri, sn, C.c_uint64(seed),
                                                 C.c_float(mel_scale), _lib.dptr(wav), B, T, _lib.current_stream()))
         return wav
 
-    def __call__(self, x, f0, **kw):
+    def __call__(self, x, f0=None, **kw):
         """Generator.forward(x [B,num_mels,T], f0 [B,T]) -> [B,1,T*hop]  (models.py:361-387)."""
         return self.forward_mel(x.transpose(1, 2), f0, 1.0, **kw)[:, None, :]
 

@@ -162,6 +162,9 @@ typedef struct {
   int32_t num_dilations;                                   /* dilations per ResBlock1 (3) */
   int32_t resblock_dilation_sizes[DSVC_NSF_MAX_KERNELS][DSVC_NSF_MAX_DILATIONS];
   int32_t harmonic_num;                                    /* 8 (models.py:334) */
+  int32_t has_source;                                      /* 1: m_source + noise_convs weights are given (NSF);
+                                                              0: plain HiFi-GAN (modules/hifigan/hifigan.py with
+                                                              use_pitch_embed = false) */
 } dsvc_nsf_config;
 
 /* HOST fp32 pointers, weight-norm already folded (remove_weight_norm, models.py:389-396),
@@ -187,10 +190,12 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
                     void* stream);
 void dsvc_nsf_destroy(dsvc_nsf_t* h);
 
-/* Generator.forward(x, f0) (models.py:361-387).
+/* Generator.forward(x, f0) (models.py:361-387); also HifiGanGenerator.forward(x, f0=None) of the 24 kHz
+ * vocoder (modules/hifigan/hifigan.py:144-169): the same network, mel_scale = 1, and f0 == NULL skips the
+ * harmonic source exactly like the reference's `if f0 is not None` branches.
  * mel: device fp32 [B, T, num_mels] log10-mel as produced by the diffusion side; it is scaled by
  *      `mel_scale` (2.30259: log10 -> ln, nsf_hifigan.py:39,65) on load;
- * f0:  device fp32 [B, T] in Hz, 0 = unvoiced;
+ * f0:  device fp32 [B, T] in Hz, 0 = unvoiced; NULL = no source (needs no has_source weights);
  * rand_ini: device fp32 [B, harmonic_num+1] replacing torch.rand at models.py:192 (column 0 is
  *      forced to 0 as at :194), or NULL -> Philox(seed);
  * sine_noise: device fp32 [B, T*hop, harmonic_num+1] replacing randn_like at models.py:271, or

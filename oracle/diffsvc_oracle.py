@@ -358,19 +358,22 @@ def nsf_generator(sd, h, mel, f0, rand_ini, noise, return_source=False):
     rks = list(h["resblock_kernel_sizes"])
     rds = list(h["resblock_dilation_sizes"])
     hop = int(np.prod(rates))
-    f0_up = torch.repeat_interleave(f0[:, None], hop, dim=2).transpose(1, 2)     # nearest upsample, :331,:363
-    har = source_module(sd, f0_up, h["sampling_rate"], 8, rand_ini, noise).transpose(1, 2)   # [B,1,L]
+    har = None
+    if f0 is not None:   # modules/hifigan/hifigan.py:145-149 skips the source without f0; the NSF generator always has it
+        f0_up = torch.repeat_interleave(f0[:, None], hop, dim=2).transpose(1, 2)     # nearest upsample, :331,:363
+        har = source_module(sd, f0_up, h["sampling_rate"], 8, rand_ini, noise).transpose(1, 2)   # [B,1,L]
     x = F.conv1d(mel, sd["conv_pre.weight"], sd["conv_pre.bias"], padding=3)    # :367
     nk = len(rks)
     for i, (u, k) in enumerate(zip(rates, ksizes)):
         x = F.leaky_relu(x, LRELU_SLOPE)
         x = F.conv_transpose1d(x, sd["ups.%d.weight" % i], sd["ups.%d.bias" % i], stride=u, padding=(k - u) // 2)
-        if i + 1 < len(rates):
-            s = int(np.prod(rates[i + 1:]))
-            xs_ = F.conv1d(har, sd["noise_convs.%d.weight" % i], sd["noise_convs.%d.bias" % i], stride=s, padding=s // 2)
-        else:
-            xs_ = F.conv1d(har, sd["noise_convs.%d.weight" % i], sd["noise_convs.%d.bias" % i])
-        x = x + xs_
+        if har is not None:
+            if i + 1 < len(rates):
+                s = int(np.prod(rates[i + 1:]))
+                xs_ = F.conv1d(har, sd["noise_convs.%d.weight" % i], sd["noise_convs.%d.bias" % i], stride=s, padding=s // 2)
+            else:
+                xs_ = F.conv1d(har, sd["noise_convs.%d.weight" % i], sd["noise_convs.%d.bias" % i])
+            x = x + xs_
         xs = None
         for j in range(nk):
             r = resblock1(sd, "resblocks.%d." % (i * nk + j), x, rks[j], rds[j])

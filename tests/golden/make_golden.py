@@ -180,6 +180,43 @@ def gen_nsf():
     print("nsf_small: wav", tuple(wav.shape), float(wav.abs().max()), float(wav.std()))
 
 
+def gen_hifigan24k():
+    """The 24 kHz vocoder's generator (modules/hifigan/hifigan.py:104-169), with and without the f0 source."""
+    import modules.hifigan.hifigan as hg
+    h = dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=16,
+             resblock_kernel_sizes=[3, 5], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]], use_pitch_embed=True,
+             audio_sample_rate=24000)
+    torch.manual_seed(77)
+    gen = hg.HifiGanGenerator(h).eval()
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith("weight_v") or (n.endswith(".weight") and "noise_convs" in n):
+                p.mul_(1.0 / (p.std() + 1e-8)).mul_(0.35 / np.sqrt(np.prod(p.shape[1:]) / (4 if n.startswith("ups") else 1)))
+            if n.endswith("weight_g"):
+                p.copy_(p * (1.0 + 0.3 * torch.randn_like(p)))
+    ckpt_sd = {k: v.clone() for k, v in gen.state_dict().items()}
+    g = torch.Generator().manual_seed(19)
+    B, T = 2, 10
+    mel = torch.randn(B, 80, T, generator=g)
+    f0 = torch.rand(B, T, generator=g) * 300 + 100
+    f0[1, 2:5] = 0
+    gen.remove_weight_norm()
+    with DrawRecorder() as rec, torch.no_grad():
+        wav_f0 = gen(mel, f0)
+    assert [k for k, _ in rec.log] == ["rand", "randn_like", "randn_like"]
+    with torch.no_grad():
+        wav_plain = gen(mel)
+    d = _np(ckpt_sd, "ckpt/")
+    d.update(mel=mel.numpy(), f0=f0.numpy(), rand_ini=rec.log[0][1].numpy(), sine_noise=rec.log[1][1].numpy(),
+             wav_f0=wav_f0.numpy(), wav_plain=wav_plain.numpy())
+    for k in ("upsample_rates", "upsample_kernel_sizes", "resblock_kernel_sizes", "resblock_dilation_sizes"):
+        d["h/" + k] = np.asarray(h[k], dtype=np.int64)
+    d["h/upsample_initial_channel"] = np.int64(16)
+    d["h/audio_sample_rate"] = np.int64(24000)
+    np.savez_compressed(os.path.join(HERE, "hifigan24k_small.npz"), **d)
+    print("hifigan24k_small: wav", tuple(wav_f0.shape), float(wav_f0.std()), float(wav_plain.std()))
+
+
 def main():
     hp = rh.install(overrides=SMALL)
     gen_diffnet(hp)
@@ -191,6 +228,7 @@ def main():
     gen_sampler(hp, "gtmel_small", K_step=1000, speedup=1, spec_min=[-5.0], spec_max=[0.0],
                 use_gt_mel=True, add_noise_step=5, seed=37)
     gen_nsf()
+    gen_hifigan24k()
 
 
 if __name__ == "__main__":

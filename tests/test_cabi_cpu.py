@@ -26,7 +26,7 @@ def test_struct_layouts_match_header():
     from diffsvc_b200 import _lib
     assert C.sizeof(_lib.DiffnetConfig) == 7 * 4
     assert C.sizeof(_lib.DiffnetWeights) == 19 * 8
-    assert C.sizeof(_lib.NsfConfig) == 4 * (4 + 8 + 8 + 1 + 8 + 1 + 64 + 1)
+    assert C.sizeof(_lib.NsfConfig) == 4 * (4 + 8 + 8 + 1 + 8 + 1 + 64 + 1 + 1)
     assert C.sizeof(_lib.NsfWeights) == 14 * 8
 
 

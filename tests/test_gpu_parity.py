@@ -322,3 +322,22 @@ def test_vocoder_checkpoint_file_roundtrip(tmp_path):
     wav = voc.spec2wav_torch(mel.to(DEV), f0=torch.from_numpy(z["f0"]).to(DEV),
                              rand_ini=torch.from_numpy(z["rand_ini"]), sine_noise=torch.from_numpy(z["sine_noise"])).cpu()
     assert (wav - torch.from_numpy(z["wav"]).reshape(-1)).abs().max().item() <= 5e-5
+
+
+def test_hifigan24k_golden():
+    """24 kHz vocoder (network/vocoders/hifigan.py + modules/hifigan/hifigan.py) on the same kernels."""
+    from diffsvc_b200.vocoders.hifigan import HifiGAN
+    z = np.load(os.path.join(GOLD, "hifigan24k_small.npz"))
+    ckpt = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ckpt/")}
+    h = {k[2:]: z[k].tolist() for k in z.files if k.startswith("h/")}
+    h.update(resblock="1", use_pitch_embed=True)
+    _hp(use_nsf=True)
+    voc = HifiGAN.from_state_dict(h, ckpt, device=DEV)
+    assert voc.model.h.num_mels == 80 and voc.model.hop == 8
+    mel, f0 = z["mel"], z["f0"]
+    for b in range(mel.shape[0]):
+        w = voc.spec2wav(mel[b].T, f0=f0[b], rand_ini=torch.from_numpy(z["rand_ini"][b:b + 1]),
+                         sine_noise=torch.from_numpy(z["sine_noise"][b:b + 1]))
+        assert np.abs(w - z["wav_f0"][b, 0]).max() <= 2e-5
+        w2 = voc.spec2wav(mel[b].T)                                        # no f0: plain HiFi-GAN path
+        assert np.abs(w2 - z["wav_plain"][b, 0]).max() <= 2e-5

@@ -83,3 +83,17 @@ def test_nsf_generator_matches_reference():
     ref = torch.from_numpy(z["wav"])
     assert wav.shape == ref.shape
     assert (wav - ref).abs().max().item() <= 2e-6
+
+
+def test_hifigan24k_generator_matches_reference():
+    """modules/hifigan/hifigan.py: same network; with the f0 source and without it (`f0=None`)."""
+    z = np.load(os.path.join(GOLD, "hifigan24k_small.npz"))
+    ckpt = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ckpt/")}
+    h = {k[2:]: (z[k].tolist()) for k in z.files if k.startswith("h/")}
+    h["sampling_rate"] = h["audio_sample_rate"]
+    sd = O.fold_weight_norm(ckpt)
+    mel, f0 = torch.from_numpy(z["mel"]), torch.from_numpy(z["f0"])
+    wav = O.nsf_generator(sd, h, mel, f0, torch.from_numpy(z["rand_ini"]), torch.from_numpy(z["sine_noise"]))
+    assert (wav - torch.from_numpy(z["wav_f0"])).abs().max().item() <= 2e-6
+    plain = O.nsf_generator(sd, h, mel, None, None, None)
+    assert (plain - torch.from_numpy(z["wav_plain"])).abs().max().item() <= 2e-6
