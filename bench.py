@@ -294,9 +294,12 @@ def main():
                 "d2h_bytes_per_step": int(h_wav.numel() * 4), "api": "GaussianDiffusion.forward + NsfHifiGAN.spec2wav_torch"},
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<EpiGate> (dilated conv + conditioner + gate, one layer)",
                      "achieved": conv_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": conv_tf / peak_burst,
-                     "traffic": None, "us_per_launch": conv_us,
-                     "note": "algorithmic fp32-equivalent FLOPs (2*3*C*2C per frame); the 3-pass fp16 split executes 3x that on "
-                             "the tensor pipe. peak = MEASURED_PEAKS.json bf16_tflops (burst)" + ("" if peaks else " [fallback]")},
+                     "traffic": 7.54e6 if (B == 1 and T == 862) else None, "us_per_launch": conv_us,
+                     "note": "algorithmic fp32-equivalent FLOPs (2*3*C*2C per frame) / CUDA-event time of the kernel run back to back; "
+                             "the error-compensated fp16 hi/lo split executes 3x those FLOPs on the tensor pipe (ceiling of frac = 0.33). "
+                             "traffic = dram bytes per launch from profiles/r1c_conv_kernel_full.md (ncu --set full; ~= the "
+                             "algorithmic 7.5 MB: weights 3.5 + conditioner 2.6 + activations 1.3). "
+                             "peak = MEASURED_PEAKS.json bf16_tflops (burst)" + ("" if peaks else " [fallback]")},
         "sampler_flops": {"achieved_tflops": sampler_flop / (ms_dev / 1000.0) / 1e12, "peak_sustained": peak_sus,
                           "note": "whole step incl. vocoder time; algorithmic DiffNet FLOPs only"},
     })

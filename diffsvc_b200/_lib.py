@@ -94,6 +94,8 @@ SYMBOLS = [
     ("dsvc_diffnet_set_schedule", C.c_int, [_VP] + [_FP] * 6),
     ("dsvc_diffnet_prepare", C.c_int, [_VP, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _VP, _VP]),
     ("dsvc_diffnet_eval", C.c_int, [_VP, _VP, C.c_int32, _VP, _VP]),
+    ("dsvc_cond_encode", C.c_int, [_VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_float, C.c_float, _VP, _VP, _VP]),
     ("dsvc_diffnet_run_layer", C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     ("dsvc_sample_ddpm", C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_uint64, _VP]),
     ("dsvc_sample_plms", C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
@@ -112,7 +114,13 @@ def load():
         return _lib
     path = os.environ.get("DSVC_LIB")        # developer override (e.g. an instrumented build)
     if not path:
-        if not os.path.exists(LIB_PATH) or (_stale() and os.path.exists("/usr/local/cuda/bin/nvcc")):
+        # Rebuild when the library is missing, or (on the GPU-less build box only) older than its sources.
+        # On a GPU box an existing library is used as shipped: N ranks must not race an nvcc rebuild.
+        need = not os.path.exists(LIB_PATH)
+        if not need and _stale() and os.path.exists("/usr/local/cuda/bin/nvcc"):
+            import torch
+            need = (not torch.cuda.is_available()) or os.environ.get("DSVC_AUTOBUILD") == "1"
+        if need:
             build()
         path = LIB_PATH
     lib = C.CDLL(path)

@@ -1,7 +1,8 @@
 """Conditioning encoder used when the reference's `modules.fastspeech.fs2.FastSpeech2` is not
-importable (stand-alone tests / bench).  It restates, in PyTorch on whatever device the inputs are
-on, the `no_fs2` path of FastSpeech2.forward (modules/fastspeech/fs2.py:94-154, add_pitch :185-238,
-utils/pitch_utils.py:17-31,63-76).  One-off per utterance: SURVEY.md section 8(f) row 1 ("next").
+importable (stand-alone tests / bench): the `no_fs2` path of FastSpeech2.forward
+(modules/fastspeech/fs2.py:94-154, add_pitch :185-238, utils/pitch_utils.py:17-31,63-76).
+SURVEY.md section 8(f) row 1: CUDA tensors go through one fused kernel (`dsvc_cond_encode`); the
+PyTorch restatement below is the host-side mirror for CPU tensors (state-dict plumbing and CPU tests).
 """
 import numpy as np
 import torch
@@ -40,6 +41,24 @@ class CondEncoder(nn.Module):
             raise NotImplementedError("stand-alone CondEncoder covers the config_nsf.yaml conditioning only; "
                                       "run inside the reference tree to use its FastSpeech2")
         ret = {"mel2ph": mel2ph}
+        if hubert.is_cuda:      # device path: one fused kernel through the C-ABI (include/dsvc.h: dsvc_cond_encode)
+            from . import _lib
+            hub = hubert.detach().to(torch.float32).contiguous()
+            m2p = mel2ph.to(torch.int64).contiguous()
+            f0c = f0.detach().to(torch.float32).contiguous()
+            emb = self.pitch_embed.weight.detach().to(hub.device, torch.float32).contiguous()
+            B, Th, H = hub.shape
+            T = m2p.shape[1]
+            out = torch.empty(B, T, H, device=hub.device, dtype=torch.float32)
+            f0d = torch.empty(B, T, device=hub.device, dtype=torch.float32)
+            _lib.check(_lib.load().dsvc_cond_encode(_lib.dptr(hub), _lib.dptr(m2p), _lib.dptr(f0c), _lib.dptr(emb), B, Th, T, H,
+                                                    int(hparams["f0_bin"]), float(hparams["f0_min"]), float(hparams["f0_max"]),
+                                                    _lib.dptr(out), _lib.dptr(f0d), _lib.current_stream()))
+            f0[mel2ph == 0] = 0                                # fs2.py:226-227 (in-place on the caller's tensor)
+            pitch_pad = None
+            ret["f0_denorm"] = f0d
+            ret["decoder_inp"] = out
+            return ret
         decoder_inp = F.pad(hubert, [0, 0, 1, 0])
         mel2ph_ = mel2ph[..., None].repeat([1, 1, hubert.shape[-1]])
         decoder_inp = torch.gather(decoder_inp, 1, mel2ph_)

@@ -44,6 +44,29 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// conditioning encoder (fs2.py:94-154 no_fs2 path): one block per (frame, item)
+__global__ void cond_encode_kernel(const float* __restrict__ hubert, const long long* __restrict__ mel2ph,
+                                   const float* __restrict__ f0, const float* __restrict__ emb, int Th, int T, int H,
+                                   int f0_bin, float mel_min, float mel_max, float* __restrict__ out,
+                                   float* __restrict__ f0_denorm) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const long long idx = mel2ph[(size_t)b * T + t];
+  const bool live = idx > 0;
+  // denorm_f0 (pitch_norm 'log'): 2 ** f0, zeroed on padding (pitch_utils.py:66-67,74-75)
+  const float den = live ? exp2f(f0[(size_t)b * T + t]) : 0.0f;
+  // f0_to_coarse (pitch_utils.py:17-31)
+  float m = mul_rn(1127.0f, logf(add_rn(1.0f, div_rn(den, 700.0f))));
+  if (m > 0.0f) m = add_rn(div_rn(mul_rn(sub_rn(m, mel_min), (float)(f0_bin - 2)), sub_rn(mel_max, mel_min)), 1.0f);
+  if (m <= 1.0f) m = 1.0f;
+  if (m > (float)(f0_bin - 1)) m = (float)(f0_bin - 1);
+  const int pitch = (int)(long long)(m + 0.5f);
+  if (threadIdx.x == 0) f0_denorm[(size_t)b * T + t] = den;
+  const float* hrow = live ? hubert + ((size_t)b * Th + (size_t)(idx - 1)) * H : nullptr;
+  const float* erow = emb + (size_t)pitch * H;
+  float* orow = out + ((size_t)b * T + t) * H;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) orow[h] = live ? add_rn(hrow[h], erow[h]) : 0.0f;
+}
+
 __global__ void set_state_kernel(StepState* st, int t, int interval) {
   st->t = t;
   st->t_prev = max(t - interval, 0);
@@ -623,6 +646,21 @@ int dsvc_diffnet_eval(dsvc_diffnet_t* h, const float* spec, int32_t t, float* ou
   DSVC_TRY(load_x(h, spec, s));
   HeadArgs ha; ha.mode = HEAD_EVAL; ha.out = out;
   return enqueue_eval(h, ha, s);
+}
+
+int dsvc_cond_encode(const float* hubert, const int64_t* mel2ph, const float* f0, const float* pitch_embed, int32_t B,
+                     int32_t Th, int32_t T, int32_t H, int32_t f0_bin, float f0_min, float f0_max, float* decoder_inp,
+                     float* f0_denorm, void* stream) {
+  DSVC_REQUIRE(hubert && mel2ph && f0 && pitch_embed && decoder_inp && f0_denorm, "dsvc_cond_encode: null argument");
+  DSVC_REQUIRE(B > 0 && Th > 0 && T > 0 && H > 0 && f0_bin > 2, "dsvc_cond_encode: bad dimensions");
+  DSVC_TRY(require_device());
+  const float mel_min = (float)(1127.0 * std::log(1.0 + (double)f0_min / 700.0));
+  const float mel_max = (float)(1127.0 * std::log(1.0 + (double)f0_max / 700.0));
+  cond_encode_kernel<<<dim3(T, B), 128, 0, (cudaStream_t)stream>>>(hubert, reinterpret_cast<const long long*>(mel2ph), f0,
+                                                                 pitch_embed, Th, T, H, f0_bin, mel_min, mel_max,
+                                                                 decoder_inp, f0_denorm);
+  DSVC_LAUNCH_CHECK();
+  return DSVC_OK;
 }
 
 int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream) {

@@ -133,6 +133,15 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
  * reset at entry and lives in the handle. */
 int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t interval, void* stream);
 
+/* Conditioning encoder, FastSpeech2.forward with no_fs2 (modules/fastspeech/fs2.py:94-154, add_pitch :185-238,
+ * utils/pitch_utils.py:17-31,63-76): decoder_inp[b][t] = (pad(hubert)[mel2ph] + pitch_embed[f0_to_coarse(2^f0)])
+ * * (mel2ph > 0).  SURVEY.md 8(f) row 1.  All pointers are device pointers:
+ * hubert fp32 [B, Th, H]; mel2ph int64 [B, T] (0 = padding, else 1-based unit index); f0 fp32 [B, T] (log2 Hz);
+ * pitch_embed fp32 [300, H]; outputs decoder_inp fp32 [B, T, H] and f0_denorm fp32 [B, T] (Hz, 0 on padding). */
+int dsvc_cond_encode(const float* hubert, const int64_t* mel2ph, const float* f0, const float* pitch_embed,
+                     int32_t B, int32_t Th, int32_t T, int32_t H, int32_t f0_bin, float f0_min, float f0_max,
+                     float* decoder_inp, float* f0_denorm, void* stream);
+
 /* Measurement hook (bench.py roofline): enqueue `iters` back-to-back launches of one kernel of the
  * WaveNet layer `layer` on the prepared workspace.  part 0 = dilated conv + conditioner + gate
  * (net.py:69-77), part 1 = output projection + residual + skip (net.py:79-84).  The workspace

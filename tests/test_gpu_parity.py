@@ -341,3 +341,23 @@ def test_hifigan24k_golden():
         assert np.abs(w - z["wav_f0"][b, 0]).max() <= 2e-5
         w2 = voc.spec2wav(mel[b].T)                                        # no f0: plain HiFi-GAN path
         assert np.abs(w2 - z["wav_plain"][b, 0]).max() <= 2e-5
+
+
+def test_cond_encoder_kernel_vs_oracle():
+    """the fused conditioning kernel against the oracle's fs2 (no_fs2) restatement."""
+    from diffsvc_b200.cond import CondEncoder
+    _hp()
+    enc = CondEncoder().to(DEV)
+    g = torch.Generator().manual_seed(4)
+    hub = torch.randn(3, 40, 256, generator=g)
+    mel2ph = torch.randint(1, 41, (3, 70), generator=g).sort(dim=1).values
+    mel2ph[2, 60:] = 0
+    f0 = torch.log2(torch.rand(3, 70, generator=g) * 900 + 45)
+    f0[0, :4] = torch.log2(torch.tensor(1500.0))                 # above f0_max: clamps to the last bin
+    dec, f0d = O.cond_encoder(enc.pitch_embed.weight.detach().cpu(), hub, mel2ph, f0.clone())
+    f0_dev = f0.clone().to(DEV)
+    ret = enc(hub.to(DEV), mel2ph.to(DEV), None, None, f0_dev, None, None)
+    assert (ret["f0_denorm"].cpu() - f0d).abs().max().item() <= 1e-3 * f0d.abs().max().item()
+    # a coarse-pitch bin may flip at an exact boundary through 1-ulp log/exp differences: allow none here (seeded)
+    assert (ret["decoder_inp"].cpu() - dec).abs().max().item() <= 1e-6
+    assert torch.equal(f0_dev.cpu()[2, 60:], torch.zeros(10))   # in-place zeroing of padded f0 (fs2.py:226-227)
