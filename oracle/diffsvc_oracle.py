@@ -310,7 +310,7 @@ def sine_gen(f0, sampling_rate, harmonic_num, rand_ini, noise, sine_amp=0.1, noi
     f0 [B,L,1] (Hz, 0 = unvoiced); rand_ini [B,dim] replaces torch.rand (:192; column 0 is zeroed
     here as at :194); noise [B,L,dim] replaces randn_like(sine_waves) (:271)."""
     dim = harmonic_num + 1
-    mult = torch.arange(1, dim + 1, dtype=f0.dtype)
+    mult = torch.arange(1, dim + 1, dtype=f0.dtype, device=f0.device)
     f0_buf = f0 * mult[None, None, :]                                   # :252-257 (f0*(idx+2))
     rad = (f0_buf / sampling_rate) % 1                                  # :188
     ri = rand_ini.clone()
