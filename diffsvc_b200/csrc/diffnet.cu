@@ -143,6 +143,7 @@ struct dsvc_diffnet {
   // persistent single-launch evaluation (tc_step.cuh): phase tables (host staging + device), grid barrier
   std::vector<StepPhase> step_host[2];
   DevBuf step_dev[2], gbar;
+  DevBuf dep_cnt;        // tile-dependency counters [B * m_tiles] (tc_gemm.cuh TcDep)
   int step_mode[2] = {-1, -1};
   int num_sms = 148;
   // CUDA graphs of one sampler step
@@ -312,6 +313,7 @@ struct HeadArgs {
   const float* noise = nullptr;
   unsigned long long seed = 0;
   int tsel = 0;   // 0: step table row st->t, 1: st->t_prev (second eval of the first PLMS iteration)
+  int dep_evals_before = 0;   // evaluations already counted in the tile-dependency counters when st->step == 0
 };
 
 static ConvGemmParams base_params(const float* A, const float* W, int B, int T, int Cin, int Cout, int taps, int dil) {
@@ -372,7 +374,7 @@ static EpiHead::Params mk_head(const dsvc_diffnet* h, const HeadArgs& ha) {
 }
 
 // K3a: dilated conv + hoisted conditioner + gate -> Z
-static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
+static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
   const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
   const int dil = 1 << (l % h->cfg.dilation_cycle_length);
   const EpiGate::Params e = mk_gate(h, l);
@@ -383,17 +385,17 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
         return tc3_launch_bn<EpiGate, 64>(m.a144_hi, m.a144_lo, m.b32_hi, m.b32_lo, e, B, T, C, 2 * C, dil, h->passes, s);
       return tc3_launch_bn<EpiGate, 128>(m.a144_hi, m.a144_lo, m.b_hi, m.b_lo, e, B, T, C, 2 * C, dil, h->passes, s);
     }
-    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s);
+    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s, dep);
   }
   const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;
   return launch_fp32<EpiGate>(h, base_params(h->Y.f32.as<float>(), W, B, T, C, 2 * C, 3, dil), e, s);
 }
 
 // K3b: output projection + residual + skip
-static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
+static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
   const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
   const EpiOutProj::Params e = mk_outproj(h, l, tsel);
-  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s);
+  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s, dep);
   const float* W = h->w_out.as<float>() + (size_t)l * 2 * C * C;
   return launch_fp32<EpiOutProj>(h, base_params(h->Z.f32.as<float>(), W, B, T, C, 2 * C, 1, 0), e, s);
 }
@@ -474,25 +476,49 @@ static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s, int
     if (slot < 0) { slot = ha.tsel ? 1 : 0; DSVC_TRY(build_step_table(h, ha, slot, s)); }
     return launch_step(h, slot, s);
   }
+  // opt-in experiment (DSVC_DATAFLOW=1, slower -- see tc_gemm.cuh TcDep): tile-level dependencies between the 2L+3
+  // tensor-core kernels; the first kernel of an evaluation keeps the full griddepcontrol.wait (it follows a plain
+  // kernel and closes the previous step)
+  static int dataflow = -1;
+  if (dataflow < 0) { const char* ev = getenv("DSVC_DATAFLOW"); dataflow = (ev && ev[0] == '1') ? 1 : 0; }
+  const bool df = h->tc && dataflow && !tc_use_halo();
+  const int n_in = tc_ctas_per_mtile(B, T, C), n_dil = tc_ctas_per_mtile(B, T, 2 * C), n_out = n_dil;
+  const int n_skip = tc_ctas_per_mtile(B, T, C), n_head = tc_ctas_per_mtile(B, T, M);
+  const int per_eval = n_in + L * (n_dil + n_out) + n_skip + n_head;
+  int done = ha.dep_evals_before * per_eval;    // CTAs per frame tile completed before the next kernel (at step 0)
+  auto dep = [&](bool first) {
+    TcDep d{nullptr, nullptr, 0, 0, 0};
+    if (df) { d.cnt = h->dep_cnt.as<int>(); d.st = h->state.as<StepState>(); d.mode = first ? 0 : 1; d.base = done; d.per_step = per_eval; }
+    return d;
+  };
   {  // K0 input_projection + ReLU
     const EpiInProj::Params e = mk_inproj(h, ha.tsel);
-    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s, dep(true)));
     else DSVC_TRY(launch_fp32<EpiInProj>(h, base_params(h->XIN.f32.as<float>(), h->w_in.as<float>(), B, T, M, C, 1, 0), e, s));
+    done += n_in;
   }
   for (int l = 0; l < L; ++l) {
-    DSVC_TRY(enqueue_layer_conv(h, l, s));
-    DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s));
+    DSVC_TRY(enqueue_layer_conv(h, l, s, dep(false)));
+    done += n_dil;
+    DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s, dep(false)));
+    done += n_out;
   }
   {  // K4a skip_projection + ReLU
     const EpiSkipProj::Params e = mk_skip(h);
-    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s, dep(false)));
     else DSVC_TRY(launch_fp32<EpiSkipProj>(h, base_params(h->SP.f32.as<float>(), h->w_skip.as<float>(), B, T, C, C, 1, 0), e, s));
+    done += n_skip;
   }
   {  // K4b output_projection + sampler update
     const EpiHead::Params e = mk_head(h, ha);
-    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s, dep(false)));
     else DSVC_TRY(launch_fp32<EpiHead>(h, base_params(h->R.f32.as<float>(), h->w_head.as<float>(), B, T, C, M, 1, 0), e, s));
   }
+  return DSVC_OK;
+}
+
+static int reset_deps(dsvc_diffnet* h, cudaStream_t s) {
+  if (h->dep_cnt.p) DSVC_CUDA(cudaMemsetAsync(h->dep_cnt.p, 0, h->dep_cnt.bytes, s));
   return DSVC_OK;
 }
 
@@ -602,6 +628,7 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
   DSVC_TRY(h->cond_cl.reserve(n * H * 4));
   DSVC_TRY(h->lengths.reserve((size_t)B * 4));
   DSVC_TRY(h->state.reserve(sizeof(StepState)));
+  DSVC_TRY(h->dep_cnt.reserve((size_t)B * ceil_div(Tmax, TC_BM) * sizeof(int)));
   if (!h->gbar.p) {
     DSVC_TRY(h->gbar.reserve(2 * sizeof(unsigned)));
     DSVC_CUDA(cudaMemsetAsync(h->gbar.p, 0, 2 * sizeof(unsigned), s));
@@ -641,6 +668,7 @@ int dsvc_diffnet_eval(dsvc_diffnet_t* h, const float* spec, int32_t t, float* ou
   if (!h->prepared) { set_error("dsvc_diffnet_eval: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
   DSVC_REQUIRE(t >= 0 && t < h->cfg.num_timesteps, "diffusion step %d outside [0,%d)", t, h->cfg.num_timesteps);
   cudaStream_t s = (cudaStream_t)stream;
+  DSVC_TRY(reset_deps(h, s));
   set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t, 0);
   DSVC_LAUNCH_CHECK();
   DSVC_TRY(load_x(h, spec, s));
@@ -668,6 +696,7 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
   if (!h->prepared) { set_error("dsvc_diffnet_run_layer: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
   DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && (part == 0 || part == 1) && iters >= 0, "bad layer/part/iters");
   cudaStream_t s = (cudaStream_t)stream;
+  DSVC_TRY(reset_deps(h, s));
   set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0, 1);   // a valid step-table row
   DSVC_LAUNCH_CHECK();
   for (int i = 0; i < iters; ++i) {
@@ -696,6 +725,7 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
   cudaStream_t s = (cudaStream_t)stream;
   DSVC_TRY(load_x(h, x, s));
   if (t_start > 0) {
+    DSVC_TRY(reset_deps(h, s));
     set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t_start - 1, 1);
     DSVC_LAUNCH_CHECK();
     HeadArgs ha; ha.mode = HEAD_DDPM; ha.noise = noise; ha.seed = seed;
@@ -729,17 +759,18 @@ int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t inter
   // reversed(range(0, t_start, interval)): first t is the largest multiple of interval below t_start
   const int n_iter = t_start > 0 ? (t_start - 1) / interval + 1 : 0;
   if (n_iter > 0) {
+    DSVC_TRY(reset_deps(h, s));
     set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), (n_iter - 1) * interval, interval);
     DSVC_LAUNCH_CHECK();
     // first iteration: two evaluations (diffusion.py:184-187)
     HeadArgs a; a.mode = HEAD_PLMS_FIRST; a.tsel = 0;
     DSVC_TRY(enqueue_eval(h, a, s));
-    HeadArgs b2; b2.mode = HEAD_PLMS_SECOND; b2.tsel = 1;
+    HeadArgs b2; b2.mode = HEAD_PLMS_SECOND; b2.tsel = 1; b2.dep_evals_before = 1;
     DSVC_TRY(enqueue_eval(h, b2, s));
     advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 1);
     DSVC_LAUNCH_CHECK();
     if (n_iter > 1) {
-      HeadArgs c; c.mode = HEAD_PLMS_NEXT;
+      HeadArgs c; c.mode = HEAD_PLMS_NEXT; c.dep_evals_before = 1;   // iteration i (st->step == i) follows i+1 evaluations
       const bool persistent = step_eligible(h);
       if (persistent) DSVC_TRY(build_step_table(h, c, 0, s));   // slot 0 held the FIRST-eval table until here
       if (!h->g_plms_valid) {

@@ -127,6 +127,50 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Tile-level dependencies between the kernels of one evaluation ("dataflow" mode).  Every CTA bumps a
+// per-(item, frame-tile) counter when its outputs are globally visible; a CTA of the NEXT kernel starts as soon as
+// ALL CTAs of the previous kernel for frame tiles m-1, m, m+1 are done (m+-1: the dilated conv's halo, and
+// the write-after-read on the plane it overwrites) instead of waiting for the whole previous grid to drain
+// (griddepcontrol.wait).  With griddepcontrol.launch_dependents at kernel entry the next kernel's CTAs are
+// already resident on the idle SMs; counters are monotonic over a sampler call:
+//   expected(kernel k, step s) = base_k + s * per_step,  base_k = CTAs per frame tile of all earlier kernels.
+// Measured (one clip, B200): correct (parity unchanged) but SLOWER than griddepcontrol.wait, 564 vs 398 us per
+// step -- the device-scope fence + atomic + polled acquire chain costs more than the hardware's grid-completion
+// path, and with one wave of equal tiles there is no tail to hide.  Opt-in: DSVC_DATAFLOW=1.
+struct TcDep {
+  int* cnt;              // [B * m_tiles]; null: no counting
+  const StepState* st;   // st->step = completed steps of this sampler call
+  int mode;              // 0: griddepcontrol.wait, 1: counters
+  int base, per_step;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one lane polls, the warp follows
+__device__ __forceinline__ void dep_wait(const TcDep& d, int b, int mt, int m_tiles, int lane) {
+  if (d.mode == 0) { pdl_wait(); return; }
+  if (lane == 0) {
+    const int expected = d.base + d.st->step * d.per_step;
+    const int lo = mt > 0 ? mt - 1 : 0, hi = mt + 1 < m_tiles ? mt + 1 : m_tiles - 1;
+    const long long t0 = clock64();
+    for (int m = lo; m <= hi; ++m) {
+      const unsigned* p = reinterpret_cast<const unsigned*>(d.cnt + b * m_tiles + m);
+      while ((int)ld_acquire_gpu_u32(p) < expected) {
+        if (clock64() - t0 > 4000000000ll) {
+          printf("libdsvc: tile dependency wait timed out (block %d,%d,%d expected %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, expected);
+          __trap();
+        }
+      }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // the producer's outputs are read by TMA (async proxy) below
+  }
+  __syncwarp();
+}
+
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -301,7 +345,7 @@ template <class Epi, int BN, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes) {
+               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes, const TcDep dep) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -423,7 +467,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
     }
     __syncwarp();
-    pdl_wait();                                 // activations below were written by the previous kernel
+    dep_wait(dep, b, (int)blockIdx.x, (int)gridDim.x, lane);   // activations below were written by the previous kernel
     if (elect_one_sync()) {
       for (int it = 0; it < pre; ++it) load_a(it, it);
     }
@@ -479,15 +523,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     TL_MARK(2);                             // all MMAs issued
   }
-  pdl_wait();   // every thread: the epilogue reads tensors the previous kernel wrote
+  dep_wait(dep, b, (int)blockIdx.x, (int)gridDim.x, lane);   // every warp: the epilogue reads tensors the previous kernel wrote
 #ifdef DSVC_TIMELINE
   tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three, tl0);
 #else
   tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three);
 #endif
   if (warp == 4) TL_MARK(6);               // epilogue done
+  if (dep.cnt != nullptr) {                // this tile's outputs are visible device-wide ...
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
+  if (dep.cnt != nullptr && threadIdx.x == 0) atomicAdd(dep.cnt + b * (int)gridDim.x + (int)blockIdx.x, 1);   // ... before it counts as done
   if constexpr (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
@@ -558,7 +607,7 @@ inline int tc_cluster_pref() {
 
 template <class Epi, int BN, int CS>
 int tc_launch_cs(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-                 cudaStream_t s) {
+                 cudaStream_t s, const TcDep& dep) {
   static bool attr_set = false;
   auto kern = tc_gemm_kernel<Epi, BN, CS>;
   if (!attr_set) {
@@ -591,23 +640,23 @@ int tc_launch_cs(const TcGemmMaps& m, const typename Epi::Params& e, int B, int 
   const CUtensorMap& bl = (BN == 64) ? m.b32_lo : (b64 ? m.b64_lo : m.b_lo);
   const CUtensorMap& ah = (CS == 1) ? m.a_hi : (CS == 2 ? m.a64_hi : m.a32_hi);
   const CUtensorMap& al = (CS == 1) ? m.a_lo : (CS == 2 ? m.a64_lo : m.a32_lo);
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, e, T, K, N, taps, dil, passes));
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, e, T, K, N, taps, dil, passes, dep));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }
 
 template <class Epi, int BN>
 int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-                 cudaStream_t s) {
+                 cudaStream_t s, const TcDep& dep) {
   const int ntiles = ceil_div(N, BN);
   // Cluster multicast of the activation tile is correct but measured neutral-to-slower: the mainloop is bound
   // by shared-memory bandwidth (TMA fill + UMMA operand reads ~ 128 B/clk/SM), which multicast does not
   // reduce.  Opt-in via DSVC_TC_CLUSTER=2|4.
   const int pref = tc_cluster_pref();
   const int cap = (pref < 0 || BN == 256) ? 1 : pref;
-  if (cap >= 4 && ntiles % 4 == 0) return tc_launch_cs<Epi, BN, 4>(m, e, B, T, K, N, taps, dil, passes, s);
-  if (cap >= 2 && ntiles % 2 == 0) return tc_launch_cs<Epi, BN, 2>(m, e, B, T, K, N, taps, dil, passes, s);
-  return tc_launch_cs<Epi, BN, 1>(m, e, B, T, K, N, taps, dil, passes, s);
+  if (cap >= 4 && ntiles % 4 == 0) return tc_launch_cs<Epi, BN, 4>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+  if (cap >= 2 && ntiles % 2 == 0) return tc_launch_cs<Epi, BN, 2>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+  return tc_launch_cs<Epi, BN, 1>(m, e, B, T, K, N, taps, dil, passes, s, dep);
 }
 
 // 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
@@ -630,13 +679,22 @@ inline bool tc_wide_tiles(int B, int T, int N) {
   return (long long)ceil_div(T, TC_BM) * (N / 256) * B >= 120;
 }
 
+// tile width the launcher will pick, and the resulting CTAs per (item, frame tile)
+inline int tc_pick_bn(int B, int T, int N) {
+  if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return 64;
+  if (tc_wide_tiles(B, T, N)) return 256;
+  return 128;
+}
+inline int tc_ctas_per_mtile(int B, int T, int N) { return ceil_div(N, tc_pick_bn(B, T, N)); }
+
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-              cudaStream_t s) {
+              cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
-  if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s);
-  if (tc_wide_tiles(B, T, N)) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s);
-  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s);
+  const int bn = tc_pick_bn(B, T, N);
+  if (bn == 64) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+  if (bn == 256) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s, dep);
 }
 
 }  // namespace dsvc
