@@ -11,5 +11,8 @@ from .diffusion import GaussianDiffusion, OfflineGaussianDiffusion  # noqa: F401
 from .vocoders.base_vocoder import VOCODERS, BaseVocoder, get_vocoder_cls, register_vocoder  # noqa: F401
 from .vocoders.nsf_hifigan import NsfHifiGAN  # noqa: F401
 from .vocoders.hifigan import HifiGAN, HifiGanGenerator  # noqa: F401
+from .vocoders.nvstft import STFT  # noqa: F401
+from .pe import PitchExtractor  # noqa: F401
+from . import infer_glue  # noqa: F401
 
 __version__ = "0.1.0"

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdsvc.so")
-SOURCES = ["api.cu", "diffnet.cu", "nsf.cu"]
+SOURCES = ["api.cu", "diffnet.cu", "nsf.cu", "mel.cu", "pe.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -82,6 +82,27 @@ class NsfWeights(C.Structure):
                 ("conv_post_w", _FP), ("conv_post_b", _FP)]
 
 
+class MelConfig(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("hop_size", C.c_int32), ("n_mels", C.c_int32), ("clip_val", C.c_float),
+                ("out_scale", C.c_float)]
+
+
+class PeConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mel_bins", "hidden_size", "predictor_hidden", "prenet_layers", "prenet_kernel",
+                                         "enc_layers", "enc_kernel", "gn_groups", "pred_layers", "pred_kernel", "pad_same",
+                                         "odim", "pos_rows", "pitch_norm", "apply_uv")] + \
+               [(n, C.c_float) for n in ("f0_mean", "f0_std", "bn_eps", "gn_eps", "ln_eps")]
+
+
+class PeWeights(C.Structure):
+    _fields_ = [("prenet_conv_w", _FPP), ("prenet_conv_b", _FPP), ("prenet_bn_w", _FPP), ("prenet_bn_b", _FPP),
+                ("prenet_bn_mean", _FPP), ("prenet_bn_var", _FPP), ("prenet_out_w", _FP), ("prenet_out_b", _FP),
+                ("enc_in_w", _FP), ("enc_in_b", _FP), ("enc_conv_w", _FPP), ("enc_conv_b", _FPP), ("enc_gn_w", _FPP),
+                ("enc_gn_b", _FPP), ("enc_out_w", _FP), ("enc_out_b", _FP), ("pred_conv_w", _FPP), ("pred_conv_b", _FPP),
+                ("pred_ln_w", _FPP), ("pred_ln_b", _FPP), ("pred_linear_w", _FP), ("pred_linear_b", _FP),
+                ("pos_table", _FP), ("pos_embed_alpha", _FP)]
+
+
 # every symbol include/dsvc.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = [
@@ -102,6 +123,12 @@ SYMBOLS = [
     ("dsvc_nsf_create", C.c_int, [C.POINTER(_VP), C.POINTER(NsfConfig), C.POINTER(NsfWeights), _VP]),
     ("dsvc_nsf_destroy", None, [_VP]),
     ("dsvc_nsf_forward", C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint64, C.c_float, _VP, C.c_int32, C.c_int32, _VP]),
+    ("dsvc_mel_frames", C.c_int64, [C.POINTER(MelConfig), C.c_int64]),
+    ("dsvc_mel_analysis", C.c_int, [C.POINTER(MelConfig), _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("dsvc_pe_create", C.c_int, [C.POINTER(_VP), C.POINTER(PeConfig), C.POINTER(PeWeights), _VP]),
+    ("dsvc_pe_destroy", None, [_VP]),
+    ("dsvc_pe_forward", C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    ("dsvc_compact_frames", C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_float, C.c_float, _VP, _VP, _VP, _VP]),
 ]
 
 _lib = None

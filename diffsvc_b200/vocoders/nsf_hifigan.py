@@ -6,6 +6,7 @@ import torch
 from ..hparams import hparams
 from .base_vocoder import BaseVocoder, register_vocoder
 from .nsf_models import Generator, load_model  # noqa: F401  (re-exported like the reference's imports)
+from .nvstft import STFT, load_wav_to_torch  # noqa: F401
 
 _CHECKS = (("sampling_rate", "audio_sample_rate"), ("num_mels", "audio_num_mel_bins"), ("n_fft", "fft_size"),
            ("win_size", "win_size"), ("hop_size", "hop_size"), ("fmin", "fmin"), ("fmax", "fmax"))
@@ -62,9 +63,28 @@ class NsfHifiGAN(BaseVocoder):
 
     @staticmethod
     def wav2spec(inp_path, device=None):
-        """Host-side mel analysis stays the reference's own code."""
-        try:
-            from network.vocoders.nsf_hifigan import NsfHifiGAN as _Ref  # type: ignore
-        except Exception as e:  # stand-alone: librosa-based nvSTFT is not available
-            raise NotImplementedError("wav2spec needs the reference's modules.nsf_hifigan.nvSTFT (host code)") from e
-        return _Ref.wav2spec(inp_path, device=device)
+        """network/vocoders/nsf_hifigan.py:75-92: (wav np[L], log10-mel np[T, M]); the analysis is one kernel."""
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        stft = _stft_for(hparams)
+        with torch.no_grad():
+            wav_torch, _ = load_wav_to_torch(inp_path, target_sr=stft.target_sr)
+            # log mel to log10 mel (0.434294) and the [T, M] transpose happen inside the kernel
+            mel_torch = stft.get_mel(wav_torch.unsqueeze(0).to(device), out_scale=0.434294, transpose=False).squeeze(0)
+            return wav_torch.cpu().numpy(), mel_torch.cpu().numpy()
+
+    def spec2wav_device(self, mel, f0, **kwargs):
+        """mel [T, M] / f0 [T] CUDA tensors -> CUDA waveform [T*hop]; `spec2wav` without the host round trip
+        (used by diffsvc_b200.infer_glue.after_infer)."""
+        return self.spec2wav_torch(mel.unsqueeze(0), f0=f0.unsqueeze(0), **kwargs)
+
+
+_STFTS = {}
+
+
+def _stft_for(hp):
+    key = tuple(hp[k] for k in ("audio_sample_rate", "audio_num_mel_bins", "fft_size", "win_size", "hop_size",
+                                "fmin", "fmax"))
+    if key not in _STFTS:
+        _STFTS[key] = STFT(*key)
+    return _STFTS[key]

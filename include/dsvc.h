@@ -214,6 +214,109 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
                      const float* sine_noise, uint64_t seed, float mel_scale, float* wav,
                      int32_t B, int32_t T, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data formats either side of the hot path
+ * ---------------------------------------------------------------------------------------- */
+
+/* Mel analysis: replaces STFT.get_mel (modules/nsf_hifigan/nvSTFT.py:72-104: reflect pad by
+ * (n_fft - hop)/2, torch.stft(center=False) with the window, sqrt(re^2 + im^2 + 1e-9), mel_basis @ spec,
+ * log(clamp(., clip_val))) and the `0.434294 *` + transpose of NsfHifiGAN.wav2spec
+ * (network/vocoders/nsf_hifigan.py:76-92). */
+typedef struct {
+  int32_t n_fft;       /* power of two in [64, 4096]; the window is given at this length */
+  int32_t hop_size;
+  int32_t n_mels;
+  float clip_val;      /* 1e-5 (nvSTFT.py:59) */
+  float out_scale;     /* 0.434294 for the log10 mel of wav2spec, 1 for get_mel's natural log */
+} dsvc_mel_config;
+
+/* frames produced for n_samples (>= 0), or -1 if the reflect padding is impossible */
+int64_t dsvc_mel_frames(const dsvc_mel_config* cfg, int64_t n_samples);
+
+/* wav: device fp32 [n_samples]; window: device fp32 [n_fft] (torch.hann_window(win_size), centre-padded
+ * to n_fft by the caller when win_size < n_fft, as torch.stft does); mel_basis: device fp32
+ * [n_mels, n_fft/2+1] (librosa.filters.mel layout); band_lo/band_hi: device int32 [n_mels], the half-open
+ * range of non-zero columns of each basis row, or both NULL for dense rows;
+ * mel_out: device fp32 [frames, n_mels]. */
+int dsvc_mel_analysis(const dsvc_mel_config* cfg, const float* wav, int64_t n_samples,
+                      const float* window, const float* mel_basis, const int32_t* band_lo,
+                      const int32_t* band_hi, float* mel_out, void* stream);
+
+/* The tensor half of Svc.after_infer (infer_tools/infer_tool.py:172-200) on the device: keep the frames
+ * with abs(mel).sum(-1) > 0, clip them to [vmin, vmax] (hparams mel_vmin / mel_vmax), and keep f0 on the
+ * same frames, so the vocoder can run on mel_out/f0_out without a host round trip.
+ * mel: device fp32 [T, M]; f0 / f0_out: device fp32 [T] or both NULL; mel_out: device fp32 [T, M] (the
+ * first *n_kept rows are written); n_kept: device int32 [1]. */
+int dsvc_compact_frames(const float* mel, const float* f0, int32_t T, int32_t M, float vmin, float vmax,
+                        float* mel_out, float* f0_out, int32_t* n_kept, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PitchExtractor (mel -> f0) of the 24 kHz models
+ * replaces modules/fastspeech/pe.py:120-149 (PitchExtractor.forward: Prenet :8-44, ConvStacks :83-117),
+ * modules/fastspeech/tts_modules.py:192-235 (PitchPredictor) and utils/pitch_utils.py:63-76 (denorm_f0),
+ * called from Svc.infer (infer_tools/infer_tool.py:164-165).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dsvc_pe dsvc_pe_t;
+
+#define DSVC_PE_MAX_LAYERS 8
+
+typedef struct {
+  int32_t n_mel_bins;        /* 80; multiple of 16 */
+  int32_t hidden_size;       /* hparams['hidden_size'] (256); multiple of 64 */
+  int32_t predictor_hidden;  /* hparams['predictor_hidden'] or hidden_size */
+  int32_t prenet_layers;     /* 3 (pe.py:9) */
+  int32_t prenet_kernel;     /* 5 */
+  int32_t enc_layers;        /* conv_layers (2); 0 = no mel_encoder */
+  int32_t enc_kernel;        /* 5 (pe.py:84) */
+  int32_t gn_groups;         /* hidden_size / 16 (pe.py:56) */
+  int32_t pred_layers;       /* 5 (pe.py:135) */
+  int32_t pred_kernel;       /* hparams['predictor_kernel'] */
+  int32_t pad_same;          /* hparams['ffn_padding'] == 'SAME' (else causal left padding) */
+  int32_t odim;              /* 2 */
+  int32_t pos_rows;          /* rows of the sinusoidal position table (>= T + 1) */
+  int32_t pitch_norm;        /* 0 none, 1 'log' (2 ** f0), 2 'standard' (f0 * f0_std + f0_mean) */
+  int32_t apply_uv;          /* pitch_type == 'frame' and hparams['use_uv'] */
+  float f0_mean, f0_std;
+  float bn_eps, gn_eps, ln_eps;   /* 1e-5, 1e-5, 1e-12 */
+} dsvc_pe_config;
+
+/* HOST fp32 pointers, PyTorch layouts (Conv1d [Cout, Cin, K], Linear [out, in]). */
+typedef struct {
+  const float* const* prenet_conv_w;   /* mel_prenet.layers.{l}.0.weight */
+  const float* const* prenet_conv_b;
+  const float* const* prenet_bn_w;     /* mel_prenet.layers.{l}.2.{weight,bias,running_mean,running_var} */
+  const float* const* prenet_bn_b;
+  const float* const* prenet_bn_mean;
+  const float* const* prenet_bn_var;
+  const float* prenet_out_w;           /* mel_prenet.out_proj */
+  const float* prenet_out_b;
+  const float* enc_in_w;               /* mel_encoder.in_proj */
+  const float* enc_in_b;
+  const float* const* enc_conv_w;      /* mel_encoder.conv.{l}.conv.conv */
+  const float* const* enc_conv_b;
+  const float* const* enc_gn_w;        /* mel_encoder.conv.{l}.norm */
+  const float* const* enc_gn_b;
+  const float* enc_out_w;              /* mel_encoder.out_proj */
+  const float* enc_out_b;
+  const float* const* pred_conv_w;     /* pitch_predictor.conv.{l}.1 */
+  const float* const* pred_conv_b;
+  const float* const* pred_ln_w;       /* pitch_predictor.conv.{l}.3 */
+  const float* const* pred_ln_b;
+  const float* pred_linear_w;          /* pitch_predictor.linear [odim, predictor_hidden] */
+  const float* pred_linear_b;
+  const float* pos_table;              /* SinusoidalPositionalEmbedding.weights [pos_rows, hidden_size], row 0 zero */
+  const float* pos_embed_alpha;        /* [1] */
+} dsvc_pe_weights;
+
+int dsvc_pe_create(dsvc_pe_t** out, const dsvc_pe_config* cfg, const dsvc_pe_weights* w, void* stream);
+void dsvc_pe_destroy(dsvc_pe_t* h);
+
+/* mel: device fp32 [B, T, n_mel_bins] (log10 mel as produced by the sampler; all-zero frames are padding);
+ * pitch_pred: device fp32 [B, T, odim] (ret['pitch_pred']); f0_denorm: device fp32 [B, T]
+ * (ret['f0_denorm_pred'], 0 on padding frames). */
+int dsvc_pe_forward(dsvc_pe_t* h, const float* mel, int32_t B, int32_t T, float* pitch_pred, float* f0_denorm,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

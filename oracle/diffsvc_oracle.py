@@ -392,6 +392,132 @@ def spec2wav(sd, h, mel_log10, f0, rand_ini, noise):
 
 
 # --------------------------------------------------------------------------------------
+# Mel analysis and the mel/f0 glue either side of the hot path
+# --------------------------------------------------------------------------------------
+
+def slaney_mel_basis(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr=, n_fft=, n_mels=, fmin=, fmax=) as called at modules/nsf_hifigan/nvSTFT.py:87.
+
+    librosa (0.9.1, requirements.txt:39) is a third-party dependency that is absent from /root/reference and
+    from this image; this is its published algorithm (Slaney's Auditory Toolbox mel scale: linear below 1 kHz
+    at 200/3 Hz per mel, log above with step ln(6.4)/27; triangles between neighbouring band edges; each filter
+    scaled by 2 / (right edge - left edge)), vectorised.  PARITY UNPINNED against librosa itself;
+    tests/test_mel_analysis.py pins it against torchaudio's independent implementation."""
+    fmax = sr / 2.0 if fmax is None else float(fmax)
+    to_mel = lambda f: np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) / (np.log(6.4) / 27.0),
+                                f * 3.0 / 200.0)   # noqa: E731
+    to_hz = lambda m: np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), m * 200.0 / 3.0)  # noqa: E731
+    edges = to_hz(np.linspace(to_mel(np.float64(fmin)), to_mel(np.float64(fmax)), n_mels + 2))   # [n_mels+2] Hz
+    freqs = np.linspace(0.0, sr / 2.0, 1 + n_fft // 2)
+    rising = (freqs[None, :] - edges[:-2, None]) / (edges[1:-1] - edges[:-2])[:, None]
+    falling = (edges[2:, None] - freqs[None, :]) / (edges[2:] - edges[1:-1])[:, None]
+    tri = np.maximum(0.0, np.minimum(rising, falling))
+    return (tri * (2.0 / (edges[2:] - edges[:-2]))[:, None]).astype(np.float32)
+
+
+def mel_analysis(y, n_fft, win_size, hop, mel_basis, clip_val=1e-5, dtype=torch.float32):
+    """STFT.get_mel, modules/nsf_hifigan/nvSTFT.py:72-104: y [B, n] -> natural-log mel [B, n_mels, frames].
+
+    `mel_basis` [n_mels, n_fft/2+1] is the matrix of :87-88; dtype=torch.float64 is the tighter arbiter."""
+    y = y.to(dtype)
+    basis = torch.as_tensor(mel_basis).to(dtype)
+    window = torch.hann_window(win_size).to(dtype)                                       # :89
+    p = int((n_fft - hop) / 2)
+    y = F.pad(y.unsqueeze(1), (p, p), mode="reflect").squeeze(1)                         # :91-92
+    spec = torch.stft(y, n_fft, hop_length=hop, win_length=win_size, window=window, center=False,
+                      normalized=False, onesided=True, return_complex=True)              # :94-95
+    spec = torch.view_as_real(spec)
+    spec = torch.sqrt(spec.pow(2).sum(-1) + 1e-9)                                        # :97
+    spec = torch.matmul(basis, spec)                                                     # :99
+    return torch.log(torch.clamp(spec, min=clip_val))                                    # :101, :55-56
+
+
+def wav2spec(wav, n_fft, win_size, hop, mel_basis, dtype=torch.float32):
+    """NsfHifiGAN.wav2spec, network/vocoders/nsf_hifigan.py:87-91: wav [n] -> log10 mel [frames, n_mels]."""
+    mel = mel_analysis(wav.unsqueeze(0), n_fft, win_size, hop, mel_basis, dtype=dtype).squeeze(0).T
+    return (0.434294 * mel) if dtype == torch.float32 else mel * 0.434294
+
+
+def after_infer_frames(mel_pred, f0_pred, vmin, vmax):
+    """The array half of Svc.after_infer, infer_tools/infer_tool.py:182-193 (numpy, B = 1 squeezed):
+    mel_pred [T, M], f0_pred [T] -> (clipped kept mel [N, M], kept f0 [N])."""
+    mask = np.abs(mel_pred).sum(-1) > 0
+    return np.clip(mel_pred[mask], vmin, vmax), f0_pred[mask]
+
+
+# --------------------------------------------------------------------------------------
+# PitchExtractor (modules/fastspeech/pe.py) -- SURVEY.md section 8f row 4
+# --------------------------------------------------------------------------------------
+
+def sinusoid_position_table(rows, dim):
+    """SinusoidalPositionalEmbedding.get_embedding(rows, dim, padding_idx=0), modules/commons/common_layers.py:105-122."""
+    half = dim // 2
+    k = math.log(10000) / (half - 1)
+    ang = torch.arange(rows, dtype=torch.float).unsqueeze(1) * torch.exp(torch.arange(half, dtype=torch.float) * -k).unsqueeze(0)
+    tab = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).view(rows, -1)
+    tab[0, :] = 0
+    return tab
+
+
+def pitch_extractor(sd, mel, conv_layers=2, pad_same=True, pitch_norm="log", use_uv=False, pitch_type="frame",
+                    f0_mean=0.0, f0_std=1.0, dtype=torch.float32):
+    """PitchExtractor.forward, modules/fastspeech/pe.py:137-149, eval mode.  sd: the module's state_dict;
+    mel [B, T, n_mel] -> (pitch_pred [B, T, 2], f0_denorm_pred [B, T])."""
+    g = lambda k: sd[k].to(dtype)   # noqa: E731
+    mel = mel.to(dtype)
+    # Prenet, pe.py:23-44
+    nonpad = 1 - mel.abs().sum(-1).eq(0).to(dtype)[:, None, :]                       # [B, 1, T]
+    x = mel.transpose(1, 2)
+    l = 0
+    while "mel_prenet.layers.%d.0.weight" % l in sd:
+        p = "mel_prenet.layers.%d." % l
+        k = sd[p + "0.weight"].shape[-1]
+        x = F.relu(F.conv1d(x, g(p + "0.weight"), g(p + "0.bias"), padding=k // 2))
+        x = F.batch_norm(x, g(p + "2.running_mean"), g(p + "2.running_var"), g(p + "2.weight"), g(p + "2.bias"),
+                         training=False, eps=1e-5)
+        x = x * nonpad
+        l += 1
+    x = F.linear(x.transpose(1, 2), g("mel_prenet.out_proj.weight"), g("mel_prenet.out_proj.bias"))
+    x = x * nonpad.transpose(1, 2)                                                   # [B, T, H]
+    # ConvStacks, pe.py:100-117
+    if conv_layers > 0:
+        x = F.linear(x, g("mel_encoder.in_proj.weight"), g("mel_encoder.in_proj.bias")).transpose(1, -1)
+        for i in range(conv_layers):
+            p = "mel_encoder.conv.%d." % i
+            k = sd[p + "conv.conv.weight"].shape[-1]
+            c = F.conv1d(x, g(p + "conv.conv.weight"), g(p + "conv.conv.bias"), padding=k // 2)
+            c = F.group_norm(c, sd[p + "norm.weight"].numel() // 16, g(p + "norm.weight"), g(p + "norm.bias"), eps=1e-5)
+            x = x + F.relu(c)
+        x = F.linear(x.transpose(1, -1), g("mel_encoder.out_proj.weight"), g("mel_encoder.out_proj.bias"))
+    # PitchPredictor, tts_modules.py:222-235
+    B, T, H = x.shape
+    tok = x[..., 0].ne(0).int()                                                      # utils/__init__.py:154-157
+    pos = (torch.cumsum(tok, dim=1).type_as(tok) * tok).long()
+    table = sinusoid_position_table(max(4096, T + 1), H).to(dtype)
+    x = x + g("pitch_predictor.pos_embed_alpha") * table.index_select(0, pos.view(-1)).view(B, T, -1)
+    x = x.transpose(1, -1)
+    i = 0
+    while "pitch_predictor.conv.%d.1.weight" % i in sd:
+        p = "pitch_predictor.conv.%d." % i
+        k = sd[p + "1.weight"].shape[-1]
+        x = F.pad(x, ((k - 1) // 2, (k - 1) // 2) if pad_same else (k - 1, 0))
+        x = F.relu(F.conv1d(x, g(p + "1.weight"), g(p + "1.bias")))
+        x = F.layer_norm(x.transpose(1, -1), (x.shape[1],), g(p + "3.weight"), g(p + "3.bias"), eps=1e-12).transpose(1, -1)
+        i += 1
+    pred = F.linear(x.transpose(1, -1), g("pitch_predictor.linear.weight"), g("pitch_predictor.linear.bias"))
+    # denorm_f0, utils/pitch_utils.py:63-76
+    f0 = pred[:, :, 0].clone()
+    if pitch_norm == "standard":
+        f0 = f0 * f0_std + f0_mean
+    if pitch_norm == "log":
+        f0 = 2 ** f0
+    if pitch_type == "frame" and use_uv:
+        f0[pred[:, :, 1] > 0] = 0
+    f0[mel.abs().sum(-1) == 0] = 0
+    return pred, f0
+
+
+# --------------------------------------------------------------------------------------
 # Deterministic synthetic parameters (no checkpoints exist in the reference repo)
 # --------------------------------------------------------------------------------------
 

@@ -22,6 +22,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_harness as rh  # noqa: E402
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import diffsvc_oracle as O  # noqa: E402  (only gen_mel uses it: the librosa mel basis stand-in)
 
 SMALL = dict(hidden_size=32, residual_layers=4, residual_channels=64, dilation_cycle_length=2,
              audio_num_mel_bins=16, keep_bins=16)
@@ -217,8 +219,92 @@ def gen_hifigan24k():
     print("hifigan24k_small: wav", tuple(wav_f0.shape), float(wav_f0.std()), float(wav_plain.std()))
 
 
+def synth_wave(n, sr, seed):
+    """a few drifting partials + a little noise, peak < 1: stands in for a vocal recording"""
+    g = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    f0 = 180.0 * 2.0 ** (0.3 * np.sin(2 * np.pi * 1.7 * t))
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    y = sum(a * np.sin(k * phase) for k, a in ((1, 0.4), (2, 0.2), (3, 0.1), (5, 0.05), (9, 0.02)))
+    y = y * (0.6 + 0.4 * np.sin(2 * np.pi * 3.1 * t)) + 0.01 * g.standard_normal(n)
+    y[: n // 10] *= 0.0005                      # a near-silent lead-in: exercises the low-energy / clip region
+    return (0.9 * y / np.abs(y).max()).astype(np.float32)
+
+
+def gen_mel():
+    """STFT.get_mel of the reference (modules/nsf_hifigan/nvSTFT.py:72-104) on CPU.  librosa is absent here, so
+    the harness serves `librosa.filters.mel` from the oracle's restatement (slaney_mel_basis): the fixture pins
+    everything downstream of the basis matrix, and stores the matrix it used."""
+    import modules.nsf_hifigan.nvSTFT as nv
+    nv.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: O.slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)
+    # nvSTFT.py:94 calls torch.stft without return_complex (torch 1.12, requirements.txt:90: a real [..., 2] view);
+    # torch 2.x demands the argument, so the harness supplies the 1.12 behaviour.
+    stft_now = torch.stft
+
+    def stft_112(*a, **k):
+        if "return_complex" in k:
+            return stft_now(*a, **k)
+        return torch.view_as_real(stft_now(*a, return_complex=True, **k))
+    nv.torch.stft = stft_112
+    d = {}
+    for tag, (sr, n_mels, n_fft, win, hop, fmin, fmax, n) in {
+            "a": (44100, 128, 2048, 2048, 512, 40, 16000, 13000),      # config_nsf.yaml
+            "b": (24000, 80, 512, 512, 128, 30, 12000, 5000),          # config.yaml (24 kHz)
+            "c": (22050, 80, 1024, 800, 256, 20, 11025, 6000)}.items():    # win_size < n_fft
+        wav = synth_wave(n, sr, seed={"a": 1, "b": 2, "c": 3}[tag])
+        stft = nv.STFT(sr, n_mels, n_fft, win, hop, fmin, fmax)
+        with torch.no_grad():
+            mel = stft.get_mel(torch.from_numpy(wav).unsqueeze(0))          # [1, n_mels, T] natural log
+        d["%s/cfg" % tag] = np.array([sr, n_mels, n_fft, win, hop, fmin, fmax], dtype=np.int64)
+        d["%s/wav" % tag] = wav
+        d["%s/mel_ln" % tag] = mel.squeeze(0).numpy()
+        d["%s/basis" % tag] = stft.mel_basis[str(fmax) + "_cpu"].numpy()
+    torch.stft = stft_now
+    np.savez_compressed(os.path.join(HERE, "mel_small.npz"), **d)
+    print("mel_small", {k: v.shape for k, v in d.items()})
+
+
+def gen_pe():
+    """PitchExtractor of the reference (modules/fastspeech/pe.py:120-149), eval mode, seeded weights with
+    non-trivial BatchNorm statistics; hidden 64 (the reference reads it from hparams)."""
+    from utils.hparams import hparams
+    import modules.fastspeech.pe as pe_mod
+    old = {k: hparams.get(k) for k in ("hidden_size", "predictor_hidden")}
+    hparams.update(hidden_size=64, predictor_hidden=-1)
+    torch.manual_seed(99)
+    m = pe_mod.PitchExtractor(n_mel_bins=80, conv_layers=2).eval()
+    with torch.no_grad():
+        for name, t in m.named_parameters():
+            if name.endswith(".bias") or ".norm." in name or ".3." in name or ".2." in name:
+                t.add_(0.1 * torch.randn_like(t))
+        for name, b in m.named_buffers():
+            if name.endswith("running_mean"):
+                b.copy_(0.2 * torch.randn_like(b))
+            if name.endswith("running_var"):
+                b.copy_(0.5 + torch.rand_like(b))
+        m.pitch_predictor.pos_embed_alpha.fill_(0.7)
+        m.pitch_predictor.linear.bias.add_(torch.tensor([7.5, 0.0]))      # log2(f0) ~ 7.5 -> ~180 Hz
+    B, T = 2, 50
+    mel = (torch.randn(B, T, 80) * 1.2 - 3.0)
+    mel[1, 37:] = 0                                                          # padding frames
+    mel[0, 11, 0] = 0
+    with torch.no_grad():
+        ret = m(mel)
+    d = {"mel": mel.numpy(), "pitch_pred": ret["pitch_pred"].numpy(), "f0_denorm_pred": ret["f0_denorm_pred"].numpy()}
+    d.update(_np(m.state_dict()))
+    np.savez_compressed(os.path.join(HERE, "pe_small.npz"), **d)
+    hparams.update(old)
+    print("pe_small", ret["pitch_pred"].shape, float(ret["f0_denorm_pred"].max()))
+
+
 def main():
     hp = rh.install(overrides=SMALL)
+    if "--only-pe" in sys.argv:
+        gen_pe()
+        return
+    if "--only-mel" in sys.argv:
+        gen_mel()
+        return
     gen_diffnet(hp)
     gen_sampler(hp, "ddpm_small", K_step=6, speedup=1, spec_min=[-5.0], spec_max=[0.0])
     per_bin_min = list(np.linspace(-6.0, -4.0, 16))
@@ -229,6 +315,8 @@ def main():
                 use_gt_mel=True, add_noise_step=5, seed=37)
     gen_nsf()
     gen_hifigan24k()
+    gen_mel()
+    gen_pe()
 
 
 if __name__ == "__main__":
