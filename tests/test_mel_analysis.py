@@ -180,7 +180,7 @@ def test_compact_frames_bit_exact(T, M, zero_every):
 @pytest.mark.gpu
 def test_after_infer_on_device_matches_host_path():
     """Svc.after_infer semantics (infer_tool.py:172-200) with CUDA tensors in the prediction dict."""
-    h = dict(O.NSF_H_44K, upsample_initial_channel=32)
+    h = dict(O.NSF_H_44K, upsample_initial_channel=128)
     sd = O.synth_nsf_weights(h, seed=5)
     D.hparams.update(use_nsf=True, mel_vmin=-6.0, mel_vmax=1.5, audio_sample_rate=44100, audio_num_mel_bins=128,
                      fft_size=2048, win_size=2048, hop_size=512, fmin=40, fmax=16000)
