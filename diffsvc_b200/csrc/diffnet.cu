@@ -92,31 +92,6 @@ __global__ void advance_state_kernel(StepState* st, int plms) {
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
-struct F16Pair {           // tcgen05 operand: fp16 hi/lo copies of a (power-of-two scaled) weight matrix
-  DevBuf hi, lo;
-  float inv_scale = 1.f;   // multiply the accumulator by this in the epilogue
-};
-
-struct PlaneBuf {
-  DevBuf f32, hi, lo;
-  Plane view(bool tc) const {
-    Plane p;
-    p.f32 = tc ? nullptr : f32.as<float>();
-    p.hi = tc ? hi.as<__half>() : nullptr;
-    p.lo = tc ? lo.as<__half>() : nullptr;
-    return p;
-  }
-  int reserve(size_t elems, bool tc) {
-    if (tc) {
-      DSVC_TRY(hi.reserve(elems * sizeof(__half)));
-      DSVC_TRY(lo.reserve(elems * sizeof(__half)));
-    } else {
-      DSVC_TRY(f32.reserve(elems * sizeof(float)));
-    }
-    return DSVC_OK;
-  }
-};
-
 }  // namespace dsvc
 
 using namespace dsvc;
@@ -165,31 +140,6 @@ namespace dsvc {
 
 static int upload_f(DevBuf& b, const std::vector<float>& v, cudaStream_t s) {
   return b.upload(v.data(), v.size() * sizeof(float), s);
-}
-
-// fp16 hi/lo split of a weight matrix with a power-of-two pre-scale that moves the weights into
-// fp16's normal range (hi + lo reproduces w * scale to ~2^-22).
-static int make_f16_pair(F16Pair& out, const float* w, size_t n, cudaStream_t s) {
-  float mx = 0.f;
-  for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(w[i]));
-  float scale = 1.f;
-  if (mx > 0.f) {
-    int e;
-    std::frexp(1024.0f / mx, &e);          // 1024/mx = m * 2^e, m in [0.5,1)
-    scale = std::ldexp(1.0f, e - 1);        // largest power of two <= 1024/mx
-  }
-  std::vector<__half> hi(n), lo(n);
-  for (size_t i = 0; i < n; ++i) {
-    const float v = w[i] * scale;
-    const __half h = __float2half_rn(v);
-    hi[i] = h;
-    lo[i] = __float2half_rn(v - __half2float(h));
-  }
-  out.inv_scale = 1.0f / scale;
-  DSVC_TRY(out.hi.upload(hi.data(), n * sizeof(__half), s));
-  DSVC_TRY(out.lo.upload(lo.data(), n * sizeof(__half), s));
-  DSVC_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
-  return DSVC_OK;
 }
 
 static int gemm_affine(const float* A, const float* W, const float* bias, float* out, int rows, int Cin, int Cout,

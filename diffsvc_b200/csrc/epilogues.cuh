@@ -464,4 +464,54 @@ struct EpiAffine {
   }
 };
 
+// ---- vocoder ResBlock convs on the tcgen05 path (modules/nsf_hifigan/models.py:57-64, :376-382) ---------------
+//   v = acc * wscale + bias;  v += res;  v = out_old + v (MRF sum);  v /= div;  out_f32 = v;
+//   act = split_f16(leaky_relu(v, slope))   -- the operand plane of the NEXT conv (its F.leaky_relu fused here)
+struct EpiVoc {
+  static constexpr bool kPair = false;
+  struct Params {
+    const float* bias;   // [Cout]
+    const float* res;    // [B][Lout][Cout] fp32 or null
+    float* out;          // [B][Lout][Cout] fp32 or null
+    Plane act;           // hi/lo planes [B][Lout][Cout] or {null}
+    int Lout, Cout;
+    int accumulate;      // out = out + v
+    float div, slope, wscale;
+  };
+  __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
+    EpiCol c;
+    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int n) {
+    const size_t idx = ((size_t)b * e.Lout + p) * e.Cout + n;
+    if (e.res) l2_prefetch_line(e.res + idx);
+    if (e.accumulate) l2_prefetch_line(e.out + idx);
+  }
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int n) {
+    EpiPre r{};
+    const size_t idx = ((size_t)b * e.Lout + p) * e.Cout + n;
+    if (e.res) r.a = *reinterpret_cast<const float4*>(e.res + idx);
+    if (e.accumulate) r.b = *reinterpret_cast<const float4*>(e.out + idx);
+    return r;
+  }
+  __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4], const EpiCol& c,
+                                               const EpiPre& r) {
+    float v[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
+    if (e.res) { v[0] = add_rn(v[0], r.a.x); v[1] = add_rn(v[1], r.a.y); v[2] = add_rn(v[2], r.a.z); v[3] = add_rn(v[3], r.a.w); }
+    if (e.accumulate) { v[0] = add_rn(r.b.x, v[0]); v[1] = add_rn(r.b.y, v[1]); v[2] = add_rn(r.b.z, v[2]); v[3] = add_rn(r.b.w, v[3]); }
+    if (e.div != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = div_rn(v[i], e.div);
+    }
+    const size_t idx = ((size_t)b * e.Lout + p) * e.Cout + n;
+    if (e.out) *reinterpret_cast<float4*>(e.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    if (e.act.hi) {
+      const float y[4] = {lrelu_(v[0], e.slope), lrelu_(v[1], e.slope), lrelu_(v[2], e.slope), lrelu_(v[3], e.slope)};
+      plane_store4(e.act, idx, y);
+    }
+  }
+};
+
 }  // namespace dsvc

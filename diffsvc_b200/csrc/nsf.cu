@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
+#include "tc_gemm.cuh"
 
 #include <memory>
 
@@ -215,15 +216,39 @@ __global__ void scale_kernel(const float* __restrict__ in, float* __restrict__ o
 struct ConvW {
   DevBuf w, b;
   int Cin = 0, Cout = 0, K = 0;
+  // tcgen05 path (ResBlock convs whose channel count tiles by 64): fp16 hi/lo weights [K][Cout][Cin] + their TMA maps
+  bool tc = false;
+  F16Pair h16;
+  CUtensorMap bh, bl, b32h, b32l;
 };
+
+// x -> fp16 (hi, lo) planes of leaky_relu(x): the operand of the first conv of every ResBlock of a stage
+__global__ void act_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n4, float slope) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  const float y[4] = {lrelu_(v.x, slope), lrelu_(v.y, slope), lrelu_(v.z, slope), lrelu_(v.w, slope)};
+  Plane pl{nullptr, hi, lo};
+  plane_store4(pl, i * 4, y);
+}
 
 }  // namespace dsvc
 
 using namespace dsvc;
 
+struct NsfStageMaps {          // activation-plane TMA maps of one upsample stage (depend on B, T)
+  bool tc = false;
+  TcGemmMaps px, pa, pt;
+};
+
 struct dsvc_nsf {
   dsvc_nsf_config cfg;
   int hop = 1;
+  bool tc_enabled = true;      // DSVC_NSF_MATH=fp32 forces the FFMA path everywhere
+  PlaneBuf PX, PA, PT;         // leaky_relu'ed operand planes: stage input, ResBlock state, conv1 output
+  std::vector<NsfStageMaps> smaps;
+  int maps_B = 0, maps_T = 0;
+  const void* maps_base = nullptr;
   DevBuf lin_w, lin_b;
   ConvW pre, post;
   std::vector<std::unique_ptr<ConvW>> ups, noise, c1, c2;
@@ -236,14 +261,23 @@ struct dsvc_nsf {
 namespace dsvc {
 
 // [Cout][Cin][K] (PyTorch Conv1d) -> [K][Cout][Cin]
-static int upload_conv(ConvW& c, const float* w, const float* b, int Cout, int Cin, int K, cudaStream_t s) {
+static int upload_conv(ConvW& c, const float* w, const float* b, int Cout, int Cin, int K, cudaStream_t s, bool tc = false) {
   std::vector<float> r((size_t)K * Cout * Cin);
   for (int co = 0; co < Cout; ++co)
     for (int ci = 0; ci < Cin; ++ci)
       for (int k = 0; k < K; ++k) r[((size_t)k * Cout + co) * Cin + ci] = w[((size_t)co * Cin + ci) * K + k];
   c.Cin = Cin; c.Cout = Cout; c.K = K;
-  DSVC_TRY(c.w.upload(r.data(), r.size() * 4, s));
   DSVC_TRY(c.b.upload(b, (size_t)Cout * 4, s));
+  c.tc = tc;
+  if (tc) {   // the tcgen05 path reads only the fp16 pair (same [tap][Cout][Cin] row order)
+    DSVC_TRY(make_f16_pair(c.h16, r.data(), r.size(), s));
+    DSVC_TRY(tc_make_b_map(&c.bh, c.h16.hi.as<__half>(), K * Cout, Cin, 128));
+    DSVC_TRY(tc_make_b_map(&c.bl, c.h16.lo.as<__half>(), K * Cout, Cin, 128));
+    DSVC_TRY(tc_make_b_map(&c.b32h, c.h16.hi.as<__half>(), K * Cout, Cin, 32));
+    DSVC_TRY(tc_make_b_map(&c.b32l, c.h16.lo.as<__half>(), K * Cout, Cin, 32));
+  } else {
+    DSVC_TRY(c.w.upload(r.data(), r.size() * 4, s));
+  }
   DSVC_CUDA(cudaStreamSynchronize(s));
   return DSVC_OK;
 }
@@ -295,6 +329,45 @@ static int conv_same(const ConvW& c, const float* in, float* out, const float* r
   return launch_affine(p, e, s);
 }
 
+// the same convolution on the tcgen05 path: `in` are the TMA maps of the (already leaky_relu'ed) operand planes
+static int conv_same_tc(const ConvW& c, const TcGemmMaps& in, EpiVoc::Params e, int B, int L, int dil, cudaStream_t s) {
+  TcGemmMaps g = in;
+  g.b_hi = c.bh; g.b_lo = c.bl; g.b32_hi = c.b32h; g.b32_lo = c.b32l;
+  e.bias = c.b.as<float>(); e.Lout = L; e.Cout = c.Cout; e.wscale = c.h16.inv_scale;
+  return tc_launch<EpiVoc>(g, e, B, L, c.Cin, c.Cout, c.K, dil, 3, s);
+}
+
+static bool nsf_tc_channels(int ch) { return ch % 64 == 0; }
+
+// (re)build the activation-plane maps for a (B, T) shape
+static int nsf_build_maps(dsvc_nsf* h, int B, int T) {
+  const dsvc_nsf_config& cfg = h->cfg;
+  if (h->maps_B == B && h->maps_T == T && h->maps_base == h->PX.hi.p) return DSVC_OK;
+  h->smaps.assign(cfg.num_upsamples, NsfStageMaps{});
+  int len = T, ch = cfg.upsample_initial_channel;
+  for (int i = 0; i < cfg.num_upsamples; ++i) {
+    len *= cfg.upsample_rates[i];
+    ch >>= 1;
+    NsfStageMaps& m = h->smaps[i];
+    m.tc = h->tc_enabled && nsf_tc_channels(ch);
+    if (!m.tc) continue;
+    auto planes = [&](TcGemmMaps& g, const PlaneBuf& pb) -> int {
+      DSVC_TRY(tc_make_a_map(&g.a_hi, pb.hi.as<__half>(), B, len, ch));
+      DSVC_TRY(tc_make_a_map(&g.a_lo, pb.lo.as<__half>(), B, len, ch));
+      DSVC_TRY(tc_make_a_map(&g.a64_hi, pb.hi.as<__half>(), B, len, ch, 64));
+      DSVC_TRY(tc_make_a_map(&g.a64_lo, pb.lo.as<__half>(), B, len, ch, 64));
+      DSVC_TRY(tc_make_a_map(&g.a32_hi, pb.hi.as<__half>(), B, len, ch, 32));
+      DSVC_TRY(tc_make_a_map(&g.a32_lo, pb.lo.as<__half>(), B, len, ch, 32));
+      return DSVC_OK;
+    };
+    DSVC_TRY(planes(m.px, h->PX));
+    DSVC_TRY(planes(m.pa, h->PA));
+    DSVC_TRY(planes(m.pt, h->PT));
+  }
+  h->maps_B = B; h->maps_T = T; h->maps_base = h->PX.hi.p;
+  return DSVC_OK;
+}
+
 }  // namespace dsvc
 
 extern "C" {
@@ -309,6 +382,10 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
   cudaStream_t s = (cudaStream_t)stream;
   std::unique_ptr<dsvc_nsf> h(new dsvc_nsf());
   h->cfg = *cfg;
+  {
+    const char* ev = getenv("DSVC_NSF_MATH");
+    h->tc_enabled = !(ev && strcmp(ev, "fp32") == 0);
+  }
   const int ns = cfg->num_upsamples, nk = cfg->num_kernels, nd = cfg->num_dilations, dim = cfg->harmonic_num + 1;
   int ch = cfg->upsample_initial_channel;
   h->hop = 1;
@@ -350,8 +427,9 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
         DSVC_REQUIRE(k % 2 == 1, "resblock kernel size %d must be odd", k);
         h->c1.emplace_back(new ConvW());
         h->c2.emplace_back(new ConvW());
-        DSVC_TRY(upload_conv(*h->c1[idx], w->convs1_w[idx], w->convs1_b[idx], cout, cout, k, s));
-        DSVC_TRY(upload_conv(*h->c2[idx], w->convs2_w[idx], w->convs2_b[idx], cout, cout, k, s));
+        const bool tc = h->tc_enabled && nsf_tc_channels(cout);
+        DSVC_TRY(upload_conv(*h->c1[idx], w->convs1_w[idx], w->convs1_b[idx], cout, cout, k, s, tc));
+        DSVC_TRY(upload_conv(*h->c2[idx], w->convs2_w[idx], w->convs2_b[idx], cout, cout, k, s, tc));
       }
     ch = cout;
   }
@@ -390,6 +468,20 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
     for (int i = 0; i < ns; ++i) { len *= cfg.upsample_rates[i]; ch >>= 1; maxact = std::max(maxact, len * ch); }
   }
   maxact *= B;
+  {
+    size_t len = T, tcact = 0;
+    int ch = cfg.upsample_initial_channel;
+    for (int i = 0; i < ns; ++i) {
+      len *= cfg.upsample_rates[i]; ch >>= 1;
+      if (h->tc_enabled && nsf_tc_channels(ch)) tcact = std::max(tcact, len * ch * (size_t)B);
+    }
+    if (tcact) {
+      DSVC_TRY(h->PX.reserve(tcact, true));
+      DSVC_TRY(h->PA.reserve(tcact, true));
+      DSVC_TRY(h->PT.reserve(tcact, true));
+    }
+    DSVC_TRY(nsf_build_maps(h, B, T));
+  }
   DSVC_TRY(h->melc.reserve((size_t)B * T * cfg.num_mels * 4));
   DSVC_TRY(h->har.reserve((size_t)B * L * 4));
   DSVC_TRY(h->S1.reserve((size_t)B * dim * T * 8));
@@ -455,6 +547,36 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
       DSVC_LAUNCH_CHECK();
     }
     // MRF: xs = sum_j ResBlock1_j(xu) / num_kernels
+    if (h->smaps[i].tc) {
+      // tcgen05 path: every conv reads fp16 (hi, lo) planes of leaky_relu(.) written by the producing epilogue
+      const NsfStageMaps& sm = h->smaps[i];
+      const size_t n4 = (size_t)B * lout * up.Cout / 4;
+      act_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(xu, h->PX.hi.as<__half>(), h->PX.lo.as<__half>(), n4, 0.1f);
+      DSVC_LAUNCH_CHECK();
+      for (int j = 0; j < nk; ++j) {
+        const float* cur = xu;
+        const TcGemmMaps* in = &sm.px;
+        for (int m = 0; m < nd; ++m) {
+          const int idx = (i * nk + j) * nd + m;
+          const int dil = cfg.resblock_dilation_sizes[j][m];
+          EpiVoc::Params e1{};
+          e1.act = h->PT.view(true); e1.div = 1.0f; e1.slope = 0.1f;
+          DSVC_TRY(conv_same_tc(*h->c1[idx], *in, e1, B, lout, dil, s));
+          EpiVoc::Params e2{};
+          e2.res = cur; e2.slope = 0.1f;
+          if (m + 1 < nd) {
+            float* nxt = (m % 2 == 0) ? h->bufR0.as<float>() : h->bufR1.as<float>();
+            e2.out = nxt; e2.act = h->PA.view(true); e2.div = 1.0f;
+            DSVC_TRY(conv_same_tc(*h->c2[idx], sm.pt, e2, B, lout, 1, s));
+            cur = nxt;
+            in = &sm.pa;
+          } else {
+            e2.out = xs; e2.accumulate = j > 0 ? 1 : 0; e2.div = (j + 1 == nk) ? (float)nk : 1.0f;
+            DSVC_TRY(conv_same_tc(*h->c2[idx], sm.pt, e2, B, lout, 1, s));
+          }
+        }
+      }
+    } else
     for (int j = 0; j < nk; ++j) {
       const float* cur = xu;
       for (int m = 0; m < nd; ++m) {

@@ -1,6 +1,6 @@
 // tcgen05 / TMA main loop for the WaveNet contractions (sm_100a only).
 //
-//   D[frame][n] = sum_{tap} sum_{k} A[b][frame + (tap-1)*dil][k] * W[tap][n][k]
+//   D[frame][n] = sum_{tap} sum_{k} A[b][frame + (tap - taps/2)*dil][k] * W[tap][n][k]     (taps odd)
 //
 // A: activation plane, channels-last fp16 (hi, lo) pair [B][T][K]  (K-major)
 // W: weight matrix fp16 (hi, lo) pair [taps*N][K]                  (K-major)
@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
+#include <cmath>
 
 #include "common.cuh"
 #include "epilogues.cuh"
@@ -44,6 +45,59 @@ struct TcMaps {
   TcGemmMaps in, skip, head;
   std::vector<TcGemmMaps> dil, out;
 };
+
+struct F16Pair {           // tcgen05 operand: fp16 hi/lo copies of a (power-of-two scaled) weight matrix
+  DevBuf hi, lo;
+  float inv_scale = 1.f;   // multiply the accumulator by this in the epilogue
+};
+
+
+struct PlaneBuf {
+  DevBuf f32, hi, lo;
+  Plane view(bool tc) const {
+    Plane p;
+    p.f32 = tc ? nullptr : f32.as<float>();
+    p.hi = tc ? hi.as<__half>() : nullptr;
+    p.lo = tc ? lo.as<__half>() : nullptr;
+    return p;
+  }
+  int reserve(size_t elems, bool tc) {
+    if (tc) {
+      DSVC_TRY(hi.reserve(elems * sizeof(__half)));
+      DSVC_TRY(lo.reserve(elems * sizeof(__half)));
+    } else {
+      DSVC_TRY(f32.reserve(elems * sizeof(float)));
+    }
+    return DSVC_OK;
+  }
+};
+
+
+// fp16 hi/lo split of a weight matrix with a power-of-two pre-scale that moves the weights into
+// fp16's normal range (hi + lo reproduces w * scale to ~2^-22).
+static inline int make_f16_pair(F16Pair& out, const float* w, size_t n, cudaStream_t s) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(w[i]));
+  float scale = 1.f;
+  if (mx > 0.f) {
+    int e;
+    std::frexp(1024.0f / mx, &e);          // 1024/mx = m * 2^e, m in [0.5,1)
+    scale = std::ldexp(1.0f, e - 1);        // largest power of two <= 1024/mx
+  }
+  std::vector<__half> hi(n), lo(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float v = w[i] * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+  out.inv_scale = 1.0f / scale;
+  DSVC_TRY(out.hi.upload(hi.data(), n * sizeof(__half), s));
+  DSVC_TRY(out.lo.upload(lo.data(), n * sizeof(__half), s));
+  DSVC_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+  return DSVC_OK;
+}
+
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
@@ -443,7 +497,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   };
   auto load_a = [&](int it, int s) {
     const int tap = it / kblocks, kb = it - tap * kblocks;
-    const int frame = m0 + (taps == 3 ? (tap - 1) * dil : 0);
+    const int frame = m0 + (tap - (taps >> 1)) * dil;   // centred odd kernel (taps = 1: the frame itself)
     if constexpr (CS == 1) {
       tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
       if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
@@ -681,6 +735,7 @@ inline bool tc_wide_tiles(int B, int T, int N) {
 
 // tile width the launcher will pick, and the resulting CTAs per (item, frame tile)
 inline int tc_pick_bn(int B, int T, int N) {
+  if (N % 128 != 0 && N % 64 == 0) return 64;        // a 128-wide tile would be half empty
   if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return 64;
   if (tc_wide_tiles(B, T, N)) return 256;
   return 128;

@@ -243,6 +243,35 @@ def test_nsf_full_vs_oracle():
     assert np.abs(w0 - ref[:L].numpy()).max() <= 5e-4
 
 
+@pytest.mark.parametrize("B,T", [(1, 7), (3, 33)])
+def test_nsf_tensor_core_path_vs_ffma_path(B, T, monkeypatch):
+    """ResBlock convs of the >= 64-channel stages run on tcgen05 (3-pass fp16 split); DSVC_NSF_MATH=fp32 keeps the
+    whole generator on the FFMA path.  Both must sit inside the waveform gate, and agree closely."""
+    from diffsvc_b200.vocoders.nsf_hifigan import NsfHifiGAN
+    _hp()
+    sd = O.synth_nsf_weights(O.NSF_H_44K, seed=77)
+    g = torch.Generator().manual_seed(B * 100 + T)
+    mel = torch.randn(B, T, 128, generator=g) * 0.8 - 2.0
+    f0 = O.synth_f0(B, T)
+    L = T * 512
+    rand_ini = torch.rand(B, 9, generator=g)
+    noise = torch.randn(B, L, 9, generator=g)
+    ref = O.spec2wav(sd, O.NSF_H_44K, mel, f0, rand_ini, noise)
+    out = {}
+    for mode in ("tc", "fp32"):
+        if mode == "fp32":
+            monkeypatch.setenv("DSVC_NSF_MATH", "fp32")
+        else:
+            monkeypatch.delenv("DSVC_NSF_MATH", raising=False)
+        voc = NsfHifiGAN.from_state_dict(dict(O.NSF_H_44K), sd, device=DEV)
+        out[mode] = voc.spec2wav_torch(mel.to(DEV), f0=f0.to(DEV), rand_ini=rand_ini, sine_noise=noise).cpu()
+        d = out[mode] - ref
+        rms = d.pow(2).mean().sqrt().item()
+        print("nsf %s B=%d T=%d: rms %.2e max %.2e" % (mode, B, T, rms, d.abs().max().item()))
+        assert rms <= 1e-4 and d.abs().max().item() <= 5e-4
+    assert (out["tc"] - out["fp32"]).abs().max().item() <= 5e-5
+
+
 def test_errors_are_loud():
     import diffsvc_b200 as D
     from diffsvc_b200 import _lib

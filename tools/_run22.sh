@@ -1,0 +1,5 @@
+mkdir -p gpurun_out; rm -f gpurun_out/*.log
+timeout 900 python -m pytest tests -m gpu -q -s -k "nsf or hifigan or vocoder or after_infer or smoke or eval_full" 2>&1 | grep -v "^$" | tail -n 30 > gpurun_out/test_voc.log
+timeout 600 python tools/dev_voc.py > gpurun_out/voc_time.log 2>&1
+timeout 300 python tools/dev_time.py tc3f16 2>&1 | grep -A2 ddpm > gpurun_out/time.log
+cat gpurun_out/test_voc.log gpurun_out/voc_time.log gpurun_out/time.log
