@@ -28,21 +28,41 @@ __device__ __forceinline__ float rad_of(float f0, int h, float sr) {
   return fmodf(div_rn(mul_rn(f0, (float)(h + 1)), sr), 1.0f);
 }
 
-// pass 1: S1[b][h][f] = sum_{f' < f} hop * rad_{f'}  (double), E[b][h] = extra of the initial phase
-__global__ void src_frames1_kernel(SrcDims d, const float* __restrict__ f0, const float* __restrict__ rand_ini,
-                                   unsigned long long seed, double* __restrict__ S1, double* __restrict__ E) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.B * d.dim) return;
-  const int b = i / d.dim, h = i % d.dim;
-  float ri = 0.f;
-  if (h > 0) ri = rand_ini ? rand_ini[b * d.dim + h] : philox_uniform(seed, 0x72616e64u, (uint64_t)b * d.dim + h);
-  const float r0 = rad_of(f0[(size_t)b * d.T], h, d.sr);
-  E[i] = (double)add_rn(r0, ri) - (double)r0;          // rad[:,0,:] += rand_ini  (models.py:195)
+// Exclusive running sum over the frames of one (item, harmonic) sequence, in the reference's order (torch's CPU
+// cumsum adds sequentially in double): a warp fetches 32 frame increments at a time and every lane replays the
+// 32 dependent adds from shuffles -- same rounding as a serial loop, without a global-memory round trip per frame.
+template <class Inc>
+__device__ __forceinline__ void warp_serial_scan(int T, double* __restrict__ dst, Inc inc_of) {
+  const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int f = 0; f < d.T; ++f) {
-    S1[(size_t)i * d.T + f] = s;
-    s += (double)d.hop * (double)rad_of(f0[(size_t)b * d.T + f], h, d.sr);
+  for (int f0i = 0; f0i < T; f0i += 32) {
+    const int f = f0i + lane;
+    const double inc = f < T ? inc_of(f) : 0.0;
+    double mine = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double v = __shfl_sync(0xffffffffu, inc, j);
+      if (lane == j) mine = s;
+      s += v;
+    }
+    if (f < T) dst[f] = mine;
   }
+}
+
+// pass 1: S1[b][h][f] = sum_{f' < f} hop * rad_{f'}  (double), E[b][h] = extra of the initial phase.  One warp per sequence.
+__global__ void __launch_bounds__(32)
+src_frames1_kernel(SrcDims d, const float* __restrict__ f0, const float* __restrict__ rand_ini,
+                   unsigned long long seed, double* __restrict__ S1, double* __restrict__ E) {
+  const int i = blockIdx.x;
+  const int b = i / d.dim, h = i % d.dim;
+  if (threadIdx.x == 0) {
+    float ri = 0.f;
+    if (h > 0) ri = rand_ini ? rand_ini[b * d.dim + h] : philox_uniform(seed, 0x72616e64u, (uint64_t)b * d.dim + h);
+    const float r0 = rad_of(f0[(size_t)b * d.T], h, d.sr);
+    E[i] = (double)add_rn(r0, ri) - (double)r0;          // rad[:,0,:] += rand_ini  (models.py:195)
+  }
+  const float* f0b = f0 + (size_t)b * d.T;
+  warp_serial_scan(d.T, S1 + (size_t)i * d.T, [&](int f) { return (double)d.hop * (double)rad_of(f0b[f], h, d.sr); });
 }
 
 // wrap flag of sample (f, k): (cumsum % 1)[n] - (cumsum % 1)[n-1] < 0   (models.py:205-207)
@@ -93,19 +113,18 @@ __global__ void src_wraps_kernel(SrcDims d, const float* __restrict__ f0, const 
   }
 }
 
-// pass 3: S2[b][h][f] = sum over earlier frames of (rad + shift)   (double)
-__global__ void src_frames2_kernel(SrcDims d, const float* __restrict__ f0, const int* __restrict__ W,
-                                   double* __restrict__ S2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.B * d.dim) return;
+// pass 3: S2[b][h][f] = sum over earlier frames of (rad + shift)   (double).  One warp per sequence.
+__global__ void __launch_bounds__(32)
+src_frames2_kernel(SrcDims d, const float* __restrict__ f0, const int* __restrict__ W, double* __restrict__ S2) {
+  const int i = blockIdx.x;
   const int b = i / d.dim, h = i % d.dim;
-  double s = 0.0;
-  for (int f = 0; f < d.T; ++f) {
-    S2[(size_t)i * d.T + f] = s;
-    const float rad = rad_of(f0[(size_t)b * d.T + f], h, d.sr);
-    const int w = W[(size_t)i * d.T + f];
-    s += (double)(d.hop - w) * (double)rad + (double)w * (double)add_rn(rad, -1.0f);
-  }
+  const float* f0b = f0 + (size_t)b * d.T;
+  const int* Wi = W + (size_t)i * d.T;
+  warp_serial_scan(d.T, S2 + (size_t)i * d.T, [&](int f) {
+    const float rad = rad_of(f0b[f], h, d.sr);
+    const int w = Wi[f];
+    return (double)(d.hop - w) * (double)rad + (double)w * (double)add_rn(rad, -1.0f);
+  });
 }
 
 // pass 4: sines, uv, additive noise, harmonic merge Linear(dim -> 1) + tanh  -> har[b][n]
@@ -158,27 +177,133 @@ __global__ void src_synth_kernel(SrcDims d, const float* __restrict__ f0, const 
 // noise_convs[i](har_source) added to the upsampled stream (models.py:370-374)
 //   x[b][p][co] += bias[co] + sum_j w[co][j] * har[b][p*s - pad + j]
 // ---------------------------------------------------------------------------------------------
-__global__ void noise_conv_add_kernel(const float* __restrict__ har, const float* __restrict__ w,
-                                      const float* __restrict__ bias, float* __restrict__ x, int Lsrc, int Lout,
-                                      int Cout, int K, int stride, int pad) {
+//   w is stored [K][Cout] (channel-contiguous: a warp's weight read is one line); a thread owns one channel and
+//   NP consecutive positions so that every weight feeds NP FMAs.
+constexpr int NOISE_PB = 32;   // positions per block
+constexpr int NOISE_NP = 4;    // positions per thread
+__global__ void __launch_bounds__(256)
+noise_conv_add_kernel(const float* __restrict__ har, const float* __restrict__ wt, const float* __restrict__ bias,
+                      float* __restrict__ x, int Lsrc, int Lout, int Cout, int K, int stride, int pad) {
   extern __shared__ float sh[];   // har window for the block's positions
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * 32;
-  const int span = 31 * stride + K;
+  const int p0 = blockIdx.x * NOISE_PB;
+  const int span = (NOISE_PB - 1) * stride + K;
   for (int i = threadIdx.x; i < span; i += blockDim.x) {
     const int n = p0 * stride - pad + i;
     sh[i] = (n >= 0 && n < Lsrc) ? har[(size_t)b * Lsrc + n] : 0.f;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * Cout; idx += blockDim.x) {
-    const int pl = idx / Cout, co = idx % Cout;
-    const int p = p0 + pl;
-    if (p >= Lout) continue;
-    float acc = 0.f;
-    const float* wr = w + (size_t)co * K;
-    for (int j = 0; j < K; ++j) acc = fmaf(__ldg(wr + j), sh[pl * stride + j], acc);
-    const size_t o = ((size_t)b * Lout + p) * Cout + co;
-    x[o] = add_rn(x[o], acc + bias[co]);
+  for (int idx = threadIdx.x; idx < (NOISE_PB / NOISE_NP) * Cout; idx += blockDim.x) {
+    const int pg = idx / Cout, co = idx % Cout;
+    const int pl = pg * NOISE_NP;
+    float acc[NOISE_NP];
+#pragma unroll
+    for (int q = 0; q < NOISE_NP; ++q) acc[q] = 0.f;
+    for (int j = 0; j < K; ++j) {
+      const float wv = __ldg(wt + (size_t)j * Cout + co);
+#pragma unroll
+      for (int q = 0; q < NOISE_NP; ++q) acc[q] = fmaf(wv, sh[(pl + q) * stride + j], acc[q]);
+    }
+    const float bv = bias[co];
+#pragma unroll
+    for (int q = 0; q < NOISE_NP; ++q) {
+      const int p = p0 + pl + q;
+      if (p < Lout) {
+        const size_t o = ((size_t)b * Lout + p) * Cout + co;
+        x[o] = add_rn(x[o], acc[q] + bv);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct convolution for the narrow stages (C = 16 / 32 channels in and out): out = conv(lrelu(in)) + bias (+ res)
+// (+ out) (/ div), the EpiAffine semantics.  The implicit GEMM is a poor fit here (N = 16 / 32: a 256 x N tile spends
+// its time staging operands).  Here a block owns 256 output frames: the leaky_relu'ed input rows (with the dilated
+// halo) are staged once in shared memory (row pitch C+4 floats: conflict-free LDS.128 for 32 consecutive rows), the
+// whole weight tensor sits next to them as [k][ci][co], and a thread owns TWO frames (t, t+128) x all C channels:
+// per (tap, ci) one broadcast LDS.128 of weights feeds 8 FMAs -- FMA-issue bound, not LDS bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_PB = 256;                  // frames per block
+template <int C>
+__global__ void __launch_bounds__(128)
+conv_small_kernel(const float* __restrict__ in, const float* __restrict__ w /* [K][C out][C in] */, const float* __restrict__ bias,
+                  const float* __restrict__ res, float* __restrict__ out, int L, int K, int dil, float in_slope, int accumulate,
+                  float div) {
+  constexpr int LD = C + 4;
+  extern __shared__ __align__(16) float sm_small[];
+  float* wsm = sm_small;                       // [K][ci][co]
+  float* xs = sm_small + K * C * C;            // [SMALL_PB + 2*halo][LD]
+  const int halo = (K >> 1) * dil;
+  const int b = blockIdx.y, p0 = blockIdx.x * SMALL_PB;
+  for (int i = threadIdx.x; i < K * C * C; i += blockDim.x) {
+    const int k = i / (C * C), r = i % (C * C), ci = r / C, co = r % C;
+    wsm[i] = __ldg(w + ((size_t)k * C + co) * C + ci);
+  }
+  const float* inb = in + (size_t)b * L * C;
+  const int rows = SMALL_PB + 2 * halo;
+  for (int i = threadIdx.x; i < rows * (C / 4); i += blockDim.x) {
+    const int r = i / (C / 4), c4 = i % (C / 4);
+    const int q = p0 - halo + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q >= 0 && q < L) {
+      v = __ldg(reinterpret_cast<const float4*>(inb + (size_t)q * C + c4 * 4));
+      if (in_slope != 1.0f) { v.x = lrelu_(v.x, in_slope); v.y = lrelu_(v.y, in_slope); v.z = lrelu_(v.z, in_slope); v.w = lrelu_(v.w, in_slope); }
+    }
+    *reinterpret_cast<float4*>(xs + (size_t)r * LD + c4 * 4) = v;
+  }
+  __syncthreads();
+  float acc[2][C];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[u][c] = 0.f;
+  const int t = threadIdx.x;
+  for (int k = 0; k < K; ++k) {
+    const float* x0 = xs + (size_t)(t + k * dil) * LD;          // frame p0 + t, tap k  (row index = t + halo + (k - K/2)*dil)
+    const float* x1 = x0 + (size_t)128 * LD;                    // frame p0 + t + 128
+    const float* wk = wsm + (size_t)k * C * C;
+#pragma unroll
+    for (int c4 = 0; c4 < C; c4 += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(x0 + c4);
+      const float4 a1 = *reinterpret_cast<const float4*>(x1 + c4);
+      const float xa[4] = {a0.x, a0.y, a0.z, a0.w}, xb[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int co = 0; co < C; co += 4) {
+          const float4 ww = *reinterpret_cast<const float4*>(wk + (c4 + i) * C + co);
+          acc[0][co] = fmaf(xa[i], ww.x, acc[0][co]); acc[0][co + 1] = fmaf(xa[i], ww.y, acc[0][co + 1]);
+          acc[0][co + 2] = fmaf(xa[i], ww.z, acc[0][co + 2]); acc[0][co + 3] = fmaf(xa[i], ww.w, acc[0][co + 3]);
+          acc[1][co] = fmaf(xb[i], ww.x, acc[1][co]); acc[1][co + 1] = fmaf(xb[i], ww.y, acc[1][co + 1]);
+          acc[1][co + 2] = fmaf(xb[i], ww.z, acc[1][co + 2]); acc[1][co + 3] = fmaf(xb[i], ww.w, acc[1][co + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int p = p0 + t + u * 128;
+    if (p >= L) continue;
+    const size_t o = ((size_t)b * L + p) * C;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+      float v[4] = {acc[u][c] + bv.x, acc[u][c + 1] + bv.y, acc[u][c + 2] + bv.z, acc[u][c + 3] + bv.w};
+      if (res) {
+        const float4 r = *reinterpret_cast<const float4*>(res + o + c);
+        v[0] = add_rn(v[0], r.x); v[1] = add_rn(v[1], r.y); v[2] = add_rn(v[2], r.z); v[3] = add_rn(v[3], r.w);
+      }
+      if (accumulate) {
+        const float4 r = *reinterpret_cast<const float4*>(out + o + c);
+        v[0] = add_rn(r.x, v[0]); v[1] = add_rn(r.y, v[1]); v[2] = add_rn(r.z, v[2]); v[3] = add_rn(r.w, v[3]);
+      }
+      if (div != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = div_rn(v[i], div);
+      }
+      *reinterpret_cast<float4*>(out + o + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
   }
 }
 
@@ -312,6 +437,9 @@ static int launch_affine(const ConvGemmParams& p, const EpiAffine::Params& e, cu
     return launch_conv_gemm_tile<64, 128, 4, 8, EpiAffine>(p, e, s);
   }
   if (p.Cout > 32) return launch_conv_gemm_tile<128, 64, 8, 4, EpiAffine>(p, e, s);
+  static int tile8 = -1;
+  if (tile8 < 0) { const char* ev = getenv("DSVC_NSF_TILE8"); tile8 = (ev && ev[0] == '1') ? 1 : 0; }
+  if (p.Cout > 16 && tile8) return launch_conv_gemm_tile<256, 32, 8, 8, EpiAffine>(p, e, s);
   if (p.Cout > 16) return launch_conv_gemm_tile<256, 32, 8, 4, EpiAffine>(p, e, s);
   return launch_conv_gemm_tile<256, 16, 4, 4, EpiAffine>(p, e, s);
 }
@@ -319,6 +447,29 @@ static int launch_affine(const ConvGemmParams& p, const EpiAffine::Params& e, cu
 // out[b][p][:] (+)= conv(lrelu(in)) + bias (+ res), dilation d, "same" padding
 static int conv_same(const ConvW& c, const float* in, float* out, const float* res, int B, int L, int dil, float slope,
                      int accumulate, float div, cudaStream_t s) {
+  static int small = -1;
+  // opt-in experiment: measured equal-to-slower than the implicit GEMM (7.05 vs 6.86 ms per 10 s clip) -- a
+  // broadcast LDS.128 still costs four shared-memory wavefronts, so the weight reads bound it, not the FMAs
+  if (small < 0) { const char* ev = getenv("DSVC_NSF_SMALLCONV"); small = (ev && ev[0] == '1') ? 1 : 0; }
+  if (small && c.Cin == c.Cout && (c.Cout == 16 || c.Cout == 32) && c.K % 2 == 1) {
+    const int halo = (c.K / 2) * dil;
+    const size_t smem = ((size_t)c.K * c.Cout * c.Cin + (size_t)(SMALL_PB + 2 * halo) * (c.Cout + 4)) * 4;
+    if (smem <= 160 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        DSVC_CUDA(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        DSVC_CUDA(cudaFuncSetAttribute(conv_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+      }
+      dim3 grid(ceil_div(L, SMALL_PB), B);
+      if (c.Cout == 16)
+        conv_small_kernel<16><<<grid, 128, smem, s>>>(in, c.w.as<float>(), c.b.as<float>(), res, out, L, c.K, dil, slope, accumulate, div);
+      else
+        conv_small_kernel<32><<<grid, 128, smem, s>>>(in, c.w.as<float>(), c.b.as<float>(), res, out, L, c.K, dil, slope, accumulate, div);
+      DSVC_LAUNCH_CHECK();
+      return DSVC_OK;
+    }
+  }
   ConvGemmParams p{};
   p.A = in; p.W = c.w.as<float>(); p.B = B; p.Lin = L; p.Cin = c.Cin; p.Cout = c.Cout; p.taps = c.K; p.rows = L;
   p.in_stride = 1; p.in_off = -((c.K * dil - dil) / 2); p.tap_step = dil; p.nphase = 1; p.tpad = 0; p.in_slope = slope;
@@ -417,7 +568,11 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
     const int Kn = (i + 1 < ns) ? 2 * rest : 1;
     h->noise[i]->Cin = 1; h->noise[i]->Cout = cout; h->noise[i]->K = Kn;
     if (cfg->has_source) {
-      DSVC_TRY(h->noise[i]->w.upload(w->noise_convs_w[i], (size_t)cout * Kn * 4, s));
+      std::vector<float> wt((size_t)Kn * cout);     // [cout][1][Kn] -> [Kn][cout]
+      for (int co = 0; co < cout; ++co)
+        for (int j = 0; j < Kn; ++j) wt[(size_t)j * cout + co] = w->noise_convs_w[i][(size_t)co * Kn + j];
+      DSVC_TRY(h->noise[i]->w.upload(wt.data(), wt.size() * 4, s));
+      DSVC_CUDA(cudaStreamSynchronize(s));
       DSVC_TRY(h->noise[i]->b.upload(w->noise_convs_b[i], (size_t)cout * 4, s));
     }
     for (int j = 0; j < nk; ++j)
@@ -499,12 +654,12 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
   if (f0) {
     SrcDims d{B, T, hop, dim, (float)cfg.sampling_rate};
     const int nseq = B * dim;
-    src_frames1_kernel<<<ceil_div(nseq, 64), 64, 0, s>>>(d, f0, rand_ini, seed, h->S1.as<double>(), h->E.as<double>());
+    src_frames1_kernel<<<nseq, 32, 0, s>>>(d, f0, rand_ini, seed, h->S1.as<double>(), h->E.as<double>());
     DSVC_LAUNCH_CHECK();
     const int bt = std::min(512, ceil_div(hop, 32) * 32);
     src_wraps_kernel<<<dim3(T, B), bt, 0, s>>>(d, f0, h->S1.as<double>(), h->E.as<double>(), h->W.as<int>());
     DSVC_LAUNCH_CHECK();
-    src_frames2_kernel<<<ceil_div(nseq, 64), 64, 0, s>>>(d, f0, h->W.as<int>(), h->S2.as<double>());
+    src_frames2_kernel<<<nseq, 32, 0, s>>>(d, f0, h->W.as<int>(), h->S2.as<double>());
     DSVC_LAUNCH_CHECK();
     src_synth_kernel<<<dim3(T, B), bt, 0, s>>>(d, f0, h->S1.as<double>(), h->S2.as<double>(), h->E.as<double>(), sine_noise,
                                                seed, h->lin_w.as<float>(), h->lin_b.as<float>(), h->har.as<float>());
@@ -541,8 +696,8 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
     if (f0) {  // x = x + noise_convs[i](har_source)
       const ConvW& nc = *h->noise[i];
       const int stride = (i + 1 < ns) ? rest : 1, pad = (i + 1 < ns) ? rest / 2 : 0;
-      const size_t shbytes = (size_t)(31 * stride + nc.K) * 4;
-      noise_conv_add_kernel<<<dim3(ceil_div(lout, 32), B), 256, shbytes, s>>>(
+      const size_t shbytes = (size_t)((NOISE_PB - 1) * stride + nc.K) * 4;
+      noise_conv_add_kernel<<<dim3(ceil_div(lout, NOISE_PB), B), 256, shbytes, s>>>(
           h->har.as<float>(), nc.w.as<float>(), nc.b.as<float>(), xu, (int)L, lout, nc.Cout, nc.K, stride, pad);
       DSVC_LAUNCH_CHECK();
     }
