@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 
 int require_device() {
+  // cudaGetDeviceProperties costs tens of milliseconds: probe each device once (the answer cannot change)
+  static std::atomic<int> verdict[64];   // 0 unknown, 1 ok, 2 wrong architecture
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && verdict[dev].load(std::memory_order_relaxed) == 1) return DSVC_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -21,7 +25,6 @@ int require_device() {
     set_error("no CUDA device visible: libdsvc has no CPU fallback (%s)", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
     return DSVC_ENODEVICE;
   }
-  int dev = 0;
   cudaDeviceProp prop;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
     cudaGetLastError();
@@ -32,6 +35,7 @@ int require_device() {
     set_error("device %d is sm_%d%d; libdsvc is built for sm_100a (B200) only", dev, prop.major, prop.minor);
     return DSVC_ENODEVICE;
   }
+  if (dev >= 0 && dev < 64) verdict[dev].store(1, std::memory_order_relaxed);
   return DSVC_OK;
 }
 

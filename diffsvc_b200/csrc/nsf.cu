@@ -437,9 +437,6 @@ static int launch_affine(const ConvGemmParams& p, const EpiAffine::Params& e, cu
     return launch_conv_gemm_tile<64, 128, 4, 8, EpiAffine>(p, e, s);
   }
   if (p.Cout > 32) return launch_conv_gemm_tile<128, 64, 8, 4, EpiAffine>(p, e, s);
-  static int tile8 = -1;
-  if (tile8 < 0) { const char* ev = getenv("DSVC_NSF_TILE8"); tile8 = (ev && ev[0] == '1') ? 1 : 0; }
-  if (p.Cout > 16 && tile8) return launch_conv_gemm_tile<256, 32, 8, 8, EpiAffine>(p, e, s);
   if (p.Cout > 16) return launch_conv_gemm_tile<256, 32, 8, 4, EpiAffine>(p, e, s);
   return launch_conv_gemm_tile<256, 16, 4, 4, EpiAffine>(p, e, s);
 }
