@@ -6,6 +6,7 @@
 #include "tc_gemm.cuh"
 #include "tc_conv3.cuh"
 #include "tc_step.cuh"
+#include "tc_splitk.cuh"
 
 #include <cmath>
 #include <memory>
@@ -119,6 +120,7 @@ struct dsvc_diffnet {
   std::vector<StepPhase> step_host[2];
   DevBuf step_dev[2], gbar;
   DevBuf dep_cnt;        // tile-dependency counters [B * m_tiles] (tc_gemm.cuh TcDep)
+  DevBuf sk_slab;        // split-K partial tiles [B][m_tiles][n_tiles][3][128][128] fp32 (tc_splitk.cuh)
   int step_mode[2] = {-1, -1};
   int num_sms = 148;
   // CUDA graphs of one sampler step
@@ -335,6 +337,10 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s, const TcDe
         return tc3_launch_bn<EpiGate, 64>(m.a144_hi, m.a144_lo, m.b32_hi, m.b32_lo, e, B, T, C, 2 * C, dil, h->passes, s);
       return tc3_launch_bn<EpiGate, 128>(m.a144_hi, m.a144_lo, m.b_hi, m.b_lo, e, B, T, C, 2 * C, dil, h->passes, s);
     }
+    // grids that leave SMs idle (one clip): one tap per CTA in a 3-CTA cluster, reduced through an L2 slab
+    if (h->passes == 3 && dep.cnt == nullptr && h->sk_slab.bytes >= tc_splitk_slab_bytes(B, T, 2 * C) &&
+        tc_splitk_eligible(B, T, 2 * C, 3, h->num_sms))
+      return tc_splitk_launch<EpiGate>(m, e, h->sk_slab.as<float>(), B, T, C, 2 * C, dil, s);
     return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s, dep);
   }
   const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;
@@ -579,6 +585,8 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
   DSVC_TRY(h->lengths.reserve((size_t)B * 4));
   DSVC_TRY(h->state.reserve(sizeof(StepState)));
   DSVC_TRY(h->dep_cnt.reserve((size_t)B * ceil_div(Tmax, TC_BM) * sizeof(int)));
+  if (tc && (2 * C) % SK_BN == 0 && (long long)ceil_div(Tmax, TC_BM) * ((2 * C) / SK_BN) * B * SK_SPLIT <= 4 * h->num_sms)
+    DSVC_TRY(h->sk_slab.reserve(tc_splitk_slab_bytes(B, Tmax, 2 * C)));
   if (!h->gbar.p) {
     DSVC_TRY(h->gbar.reserve(2 * sizeof(unsigned)));
     DSVC_CUDA(cudaMemsetAsync(h->gbar.p, 0, 2 * sizeof(unsigned), s));

@@ -192,15 +192,34 @@ def test_ragged_batch_is_per_item(math_mode):
         assert err <= 2e-4, (math_mode, b, err)
 
 
-def test_batch_composition_invariance():
-    """Size-independent property at the BASELINE shape [B,128,1000]: an item's result does not depend on its batch."""
-    gd, sd = _full_model("tc3f16")
+def test_batch_composition_invariance(monkeypatch):
+    """Size-independent property at the BASELINE shape [B,128,1000]: an item's result does not depend on its batch.
+
+    Default tile selection: every contraction keeps one K-chain regardless of the grid -> bit-identical.
+    With the opt-in split-K conv kernel (DSVC_SPLITK=1: one tap per CTA of a 3-CTA cluster, partial tiles added
+    afterwards) a single clip and a 3-clip batch differ in fp32 summation order -> equal to rounding, and the
+    reduction order is fixed -> still deterministic."""
     cond, x0, noise = _inputs(3, 1000, 3, seed=5)
-    full = gd.sample(x0.to(DEV), cond.to(DEV), 3, None, noise.to(DEV)).cpu()
-    one = gd.sample(x0[1:2].to(DEV), cond[1:2].to(DEV), 3, None, noise[:, 1:2].contiguous().to(DEV)).cpu()
-    assert torch.equal(full[1:2], one)
-    again = gd.sample(x0.to(DEV), cond.to(DEV), 3, None, noise.to(DEV)).cpu()
-    assert torch.equal(full, again)            # deterministic
+
+    def run(gd):
+        full = gd.sample(x0.to(DEV), cond.to(DEV), 3, None, noise.to(DEV)).cpu()
+        one = gd.sample(x0[1:2].to(DEV), cond[1:2].to(DEV), 3, None, noise[:, 1:2].contiguous().to(DEV)).cpu()
+        again = gd.sample(x0.to(DEV), cond.to(DEV), 3, None, noise.to(DEV)).cpu()
+        assert torch.equal(full, again)            # deterministic
+        return full, one
+
+    monkeypatch.delenv("DSVC_SPLITK", raising=False)
+    gd0, sd = _full_model("tc3f16")
+    full0, one0 = run(gd0)
+    assert torch.equal(full0[1:2], one0)
+    monkeypatch.setenv("DSVC_SPLITK", "1")
+    gd1, _ = _full_model("tc3f16")
+    full1, one1 = run(gd1)
+    assert torch.equal(full1, full0)               # the 3-clip grid is too large for split-K: same kernels
+    assert not torch.equal(one1, one0)             # the single clip did take the split-K kernel ...
+    assert (one1 - one0).abs().max().item() <= 2e-5 * one0.abs().max().item()     # ... same math, other order
+    one1b = gd1.sample(x0[1:2].to(DEV), cond[1:2].to(DEV), 3, None, noise[:, 1:2].contiguous().to(DEV)).cpu()
+    assert torch.equal(one1, one1b)
 
 
 def test_philox_stream_is_seeded():
