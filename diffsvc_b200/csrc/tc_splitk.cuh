@@ -208,14 +208,19 @@ tc_splitk_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
 // Measured (one 862-frame clip, B200): parity-clean and the kernel itself is 16 % faster run back to back (11.76 ->
 // 9.93 us, 130 -> 154 TFLOP/s algorithmic), but the 1000-step sampler does not move (409 vs 406 us per step): with 126
 // of 148 SMs holding a 197 KB CTA, the next kernel's CTAs can no longer pre-launch on idle SMs, so the PDL overlap of
-// its prologue + weight prefetch -- which is what hid the kernel boundary -- is lost.  Opt-in: DSVC_SPLITK=1 (then
-// used whenever the 3x larger grid still fits one wave); DSVC_SPLITK=2 forces it for any grid.
+// its prologue + weight prefetch -- which is what hid the kernel boundary -- is lost.
+// Hence the automatic rule: split only when the 3x larger conv grid AND the next kernel's grid (64-wide tiles) fit
+// the GPU together, i.e. short clips / real-time chunks (<= 4 frame tiles in flight).
+// DSVC_SPLITK=0 never, =1 whenever the 3x grid alone fits one wave, =2 always.
 inline bool tc_splitk_eligible(int B, int T, int N, int taps, int num_sms) {
   const char* ev = getenv("DSVC_SPLITK");          // read per call (graph capture time): tests switch it per handle
-  const int env = ev ? atoi(ev) : 0;
-  if (env <= 0 || taps != SK_SPLIT || N % SK_BN != 0) return false;
+  const int env = ev ? atoi(ev) : -1;
+  if (env == 0 || taps != SK_SPLIT || N % SK_BN != 0) return false;
   if (env >= 2) return true;
-  return (long long)ceil_div(T, TC_BM) * (N / SK_BN) * B * SK_SPLIT <= num_sms;
+  const long long mt = (long long)ceil_div(T, TC_BM) * B;
+  const long long conv_ctas = mt * (N / SK_BN) * SK_SPLIT, next_ctas = mt * (N / 64);
+  if (env == 1) return conv_ctas <= num_sms;
+  return conv_ctas + next_ctas <= num_sms;
 }
 
 inline size_t tc_splitk_slab_bytes(int B, int T, int N) {
