@@ -43,6 +43,21 @@ def test_no_cpu_fallback():
     assert rc == -3 and b"no CPU fallback" in lib.dsvc_last_error()
     with pytest.raises(_lib.DsvcError):
         D.DiffNet(128).handle()
+    # every other compute entry point refuses as well (dummy non-null pointers: the device probe comes first)
+    buf = (C.c_float * 4096)()
+    ptr = C.cast(buf, C.c_void_p)
+    mcfg = _lib.MelConfig(64, 16, 8, 1e-5, 1.0)
+    assert lib.dsvc_mel_analysis(C.byref(mcfg), ptr, 1024, ptr, ptr, None, None, ptr, None) == -3
+    assert lib.dsvc_compact_frames(ptr, None, 4, 8, -6.0, 1.5, ptr, None, ptr, None) == -3
+    assert lib.dsvc_cond_encode(ptr, ptr, ptr, ptr, 1, 4, 4, 8, 256, 40.0, 1100.0, ptr, ptr, None) == -3
+    ncfg, nw = _lib.NsfConfig(), _lib.NsfWeights()
+    ncfg.num_upsamples, ncfg.num_kernels, ncfg.num_dilations, ncfg.harmonic_num = 1, 1, 1, 8
+    assert lib.dsvc_nsf_create(C.byref(h), C.byref(ncfg), C.byref(nw), None) == -3
+    pcfg, pw = _lib.PeConfig(), _lib.PeWeights()
+    assert lib.dsvc_pe_create(C.byref(h), C.byref(pcfg), C.byref(pw), None) == -3
+    assert b"no CPU fallback" in lib.dsvc_last_error()
+    with pytest.raises(_lib.DsvcError):
+        D.PitchExtractor().handle()
 
 
 def test_state_dict_keys_match_reference_layout():
