@@ -84,3 +84,47 @@ def test_full_nsf_generator(hp):
     assert wav.shape == ref.shape == (1, 1, L)
     assert float(ref.std()) > 1e-3                      # not vacuous
     assert (wav - ref).abs().max().item() <= 5e-6
+
+
+def test_full_pitch_extractor(hp):
+    """PitchExtractor at the real size (hidden 256, 80 mel bins), eval mode, perturbed BatchNorm statistics."""
+    import modules.fastspeech.pe as pe_mod
+    torch.manual_seed(21)
+    m = pe_mod.PitchExtractor(n_mel_bins=80, conv_layers=2).eval()
+    with torch.no_grad():
+        for name, b in m.named_buffers():
+            if name.endswith("running_mean"):
+                b.copy_(0.2 * torch.randn_like(b))
+            if name.endswith("running_var"):
+                b.copy_(0.5 + torch.rand_like(b))
+        m.pitch_predictor.linear.bias.add_(torch.tensor([7.0, 0.0]))
+    mel = torch.randn(2, 120, 80) - 3.0
+    mel[1, 100:] = 0
+    with torch.no_grad():
+        ret = m(mel)
+    pred, f0 = O.pitch_extractor(m.state_dict(), mel)
+    assert (pred - ret["pitch_pred"]).abs().max().item() <= 1e-5
+    assert (f0 - ret["f0_denorm_pred"]).abs().max().item() <= 1e-3
+    assert (f0[1, 100:] == 0).all()
+
+
+def test_full_mel_analysis(hp):
+    """STFT.get_mel at config_nsf.yaml's analysis parameters (2048 / 512 / 128 bins, 40-16000 Hz).  librosa is
+    absent: the harness serves librosa.filters.mel from the oracle's restatement (see tests/golden/make_golden.py)."""
+    import modules.nsf_hifigan.nvSTFT as nv
+    nv.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: O.slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)
+    stft_now = torch.stft
+    nv.torch.stft = lambda *a, **k: stft_now(*a, **k) if "return_complex" in k else torch.view_as_real(stft_now(*a, return_complex=True, **k))
+    try:
+        g = torch.Generator().manual_seed(4)
+        wav = (torch.rand(1, 30000, generator=g) * 2 - 1) * 0.3
+        stft = nv.STFT(hp["audio_sample_rate"], hp["audio_num_mel_bins"], hp["fft_size"], hp["win_size"], hp["hop_size"],
+                       hp["fmin"], hp["fmax"])
+        with torch.no_grad():
+            ref = stft.get_mel(wav)
+    finally:
+        torch.stft = stft_now
+    basis = O.slaney_mel_basis(hp["audio_sample_rate"], hp["fft_size"], hp["audio_num_mel_bins"], hp["fmin"], hp["fmax"])
+    got = O.mel_analysis(wav, hp["fft_size"], hp["win_size"], hp["hop_size"], basis)
+    assert got.shape == ref.shape == (1, 128, 30000 // 512)
+    assert (got - ref).abs().max().item() <= 1e-5
