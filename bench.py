@@ -303,7 +303,7 @@ def main():
         "sampler_flops": {"achieved_tflops": sampler_flop / (ms_dev / 1000.0) / 1e12, "peak_sustained": peak_sus,
                           "note": "whole step incl. vocoder time; algorithmic DiffNet FLOPs only"},
     })
-    if rank == 0:
+    if rank == 0 and world == 1:      # the CPU baseline is reported at N = 1 only (the other ranks would idle at the barrier)
         threads = cpu_threads_autotune(sd, T)
         td, tv = cpu_sample(sd, nsd, T, args.ref_ddpm_sample, seed=5)
         per_clip = td / args.ref_ddpm_sample * NS + tv
@@ -311,6 +311,7 @@ def main():
                                 "sample": "%d of %d DDPM steps (%.2f s) + 1 NSF-HiFiGAN pass (%.2f s) of one %d-frame clip, DDPM part "
                                           "extrapolated linearly; oracle port of the reference modules, torch CPU fp32, %d threads"
                                           % (args.ref_ddpm_sample, NS, td, tv, T, threads)}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

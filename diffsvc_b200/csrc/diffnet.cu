@@ -7,6 +7,7 @@
 #include "tc_conv3.cuh"
 #include "tc_step.cuh"
 #include "tc_splitk.cuh"
+#include "tc_layer.cuh"
 
 #include <cmath>
 #include <memory>
@@ -115,6 +116,9 @@ struct dsvc_diffnet {
   bool prepared = false;
   DevBuf X, S, XS, hist, CP, cond_cl, lengths, state;
   PlaneBuf Y, Z, SP, R, XIN;
+  PlaneBuf Y2;           // fused-layer mode (tc_layer.cuh): conv-input plane of the odd layers (Y holds the even ones)
+  bool pingpong = false; // Y / Y2 alternate by layer parity: a layer's out-proj never overwrites the plane its conv reads
+  int fused_usable = 0;  // 1: a cluster of 2C/64 CTAs of tc_layer_kernel is schedulable on this device (probed in prepare)
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
   // persistent single-launch evaluation (tc_step.cuh): phase tables (host staging + device), grid barrier
   std::vector<StepPhase> step_host[2];
@@ -127,6 +131,7 @@ struct dsvc_diffnet {
   cudaGraphExec_t g_ddpm = nullptr, g_plms = nullptr;
   cudaStream_t cap_stream = nullptr;   // private stream used only to record graphs (the caller's may be the
                                        // legacy default stream, which cannot be captured)
+  uint64_t g_ddpm_nodes = 0, g_plms_nodes = 0;   // kernels per replay of each graph
   const float* g_ddpm_noise = nullptr;
   unsigned long long g_ddpm_seed = 0;
   bool g_ddpm_valid = false, g_plms_valid = false;
@@ -250,9 +255,10 @@ static int tc_build_maps(dsvc_diffnet* h) {
   h->maps.dil.resize(L);
   h->maps.out.resize(L);
   for (int l = 0; l < L; ++l) {
-    DSVC_TRY(gemm(h->maps.dil[l], h->Y, C, *h->h_dil[l], 3 * 2 * C));
-    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_hi, h->Y.hi.as<__half>(), B, T, C));
-    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_lo, h->Y.lo.as<__half>(), B, T, C));
+    const PlaneBuf& yin = (h->pingpong && (l & 1)) ? h->Y2 : h->Y;
+    DSVC_TRY(gemm(h->maps.dil[l], yin, C, *h->h_dil[l], 3 * 2 * C));
+    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_hi, yin.hi.as<__half>(), B, T, C));
+    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_lo, yin.lo.as<__half>(), B, T, C));
     DSVC_TRY(gemm(h->maps.out[l], h->Z, C, *h->h_out[l], 2 * C));
   }
   return DSVC_OK;
@@ -303,7 +309,8 @@ static EpiOutProj::Params mk_outproj(const dsvc_diffnet* h, int l, int tsel) {
   const int C = h->cfg.residual_channels;
   EpiOutProj::Params e{};
   e.bias = h->b_out.as<float>() + (size_t)l * 2 * C; e.dtab = h->dtab.as<float>(); e.st = h->state.as<StepState>();
-  e.lengths = h->lengths.as<int>(); e.X = h->X.as<float>(); e.S = h->S.as<float>(); e.Y = h->Y.view(h->tc); e.SP = h->SP.view(h->tc);
+  e.lengths = h->lengths.as<int>(); e.X = h->X.as<float>(); e.S = h->S.as<float>(); e.SP = h->SP.view(h->tc);
+  e.Y = ((h->pingpong && ((l + 1) & 1)) ? h->Y2 : h->Y).view(h->tc);   // the plane layer l+1's conv reads
   e.Tmax = h->Tmax; e.C = C; e.L = h->cfg.residual_layers; e.layer = l; e.tsel = tsel; e.fast = h->tc ? 1 : 0;
   e.wscale = h->tc ? h->h_out[l]->inv_scale : 1.f;
   return e;
@@ -354,6 +361,19 @@ static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s, c
   if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s, dep);
   const float* W = h->w_out.as<float>() + (size_t)l * 2 * C * C;
   return launch_fp32<EpiOutProj>(h, base_params(h->Z.f32.as<float>(), W, B, T, C, 2 * C, 1, 0), e, s);
+}
+
+// K3a + K3b as one kernel (tc_layer.cuh): a cluster of 2C/64 CTAs per frame tile, cluster barrier between the conv
+// and the output projection.
+static int enqueue_layer_fused(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
+  const int dil = 1 << (l % h->cfg.dilation_cycle_length);
+  return tc_layer_launch(h->maps.dil[l], h->maps.out[l], mk_gate(h, l), mk_outproj(h, l, tsel), h->B, h->Tmax,
+                         h->cfg.residual_channels, dil, h->passes, s);
+}
+
+static bool fused_layers(const dsvc_diffnet* h) {
+  return h->tc && h->pingpong && h->fused_usable == 1 && !tc_use_halo() &&
+         tc_layer_shape_ok(h->B, h->Tmax, h->cfg.residual_channels);
 }
 
 // ---- persistent single-launch evaluation (tc_step.cuh) -----------------------------------------
@@ -454,6 +474,10 @@ static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s, int
     done += n_in;
   }
   for (int l = 0; l < L; ++l) {
+    if (!df && fused_layers(h)) {
+      DSVC_TRY(enqueue_layer_fused(h, l, ha.tsel, s));
+      continue;
+    }
     DSVC_TRY(enqueue_layer_conv(h, l, s, dep(false)));
     done += n_dil;
     DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s, dep(false)));
@@ -498,13 +522,17 @@ static int store_x(dsvc_diffnet* h, float* x, cudaStream_t s) {
 
 // capture `body` (which enqueues on s) into an executable graph
 template <class F>
-static int capture_graph(dsvc_diffnet* h, cudaGraphExec_t* exec, F body) {
+static int capture_graph(dsvc_diffnet* h, cudaGraphExec_t* exec, uint64_t* nodes, F body) {
   if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+  const uint64_t before = g_launches.load(std::memory_order_relaxed);
   if (!h->cap_stream) DSVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   cudaStream_t s = h->cap_stream;
   cudaGraph_t g = nullptr;
   DSVC_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int r = body(s);
+  // recording is not launching: the kernels recorded here are counted per replay (dsvc_launch_count)
+  *nodes = g_launches.load(std::memory_order_relaxed) - before;
+  g_launches.fetch_sub(*nodes, std::memory_order_relaxed);
   cudaError_t ce = cudaStreamEndCapture(s, &g);
   if (r != DSVC_OK) { if (g) cudaGraphDestroy(g); return r; }
   DSVC_CUDA(ce);
@@ -538,6 +566,7 @@ int dsvc_diffnet_create(dsvc_diffnet_t** out, const dsvc_diffnet_config* cfg, co
   h->cfg = *cfg;
   h->tc = cfg->math != DSVC_MATH_FP32;
   h->passes = cfg->math == DSVC_MATH_TC1F16 ? 1 : 3;
+  h->pingpong = h->tc && tc_layer_env() > 0;     // fused-layer mode needs the conv-input plane double-buffered
   int r = build(h, w, (cudaStream_t)stream);
   if (r != DSVC_OK) { delete h; return r; }
   *out = h;
@@ -596,6 +625,10 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
     for (int i = 0; i < 2; ++i) DSVC_TRY(h->step_dev[i].reserve((size_t)(2 * L + 3) * sizeof(StepPhase)));
   }
   DSVC_TRY(h->Y.reserve(n * C, tc));
+  if (h->pingpong) {
+    DSVC_TRY(h->Y2.reserve(n * C, tc));
+    DSVC_TRY(tc_layer_probe((2 * C) / LY_BN, &h->fused_usable));
+  }
   DSVC_TRY(h->Z.reserve(n * C, tc));
   DSVC_TRY(h->SP.reserve(n * C, tc));
   DSVC_TRY(h->R.reserve(n * C, tc));
@@ -652,14 +685,20 @@ int dsvc_cond_encode(const float* hubert, const int64_t* mel2ph, const float* f0
 int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream) {
   DSVC_REQUIRE(h, "dsvc_diffnet_run_layer: null handle");
   if (!h->prepared) { set_error("dsvc_diffnet_run_layer: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
-  DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && (part == 0 || part == 1) && iters >= 0, "bad layer/part/iters");
+  DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && part >= 0 && part <= 2 && iters >= 0, "bad layer/part/iters");
+  if (part == 2 && !fused_layers(h)) {
+    set_error("dsvc_diffnet_run_layer: part 2 (fused layer kernel) needs DSVC_FUSED_LAYER and a tensor-core handle whose "
+              "2C/64 channel tiles form a schedulable cluster");
+    return DSVC_ESTATE;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   DSVC_TRY(reset_deps(h, s));
   set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0, 1);   // a valid step-table row
   DSVC_LAUNCH_CHECK();
   for (int i = 0; i < iters; ++i) {
     if (part == 0) DSVC_TRY(enqueue_layer_conv(h, layer, s));
-    else DSVC_TRY(enqueue_layer_out(h, layer, 0, s));
+    else if (part == 1) DSVC_TRY(enqueue_layer_out(h, layer, 0, s));
+    else DSVC_TRY(enqueue_layer_fused(h, layer, 0, s));
   }
 #ifdef DSVC_TIMELINE
   if (h->tc) {
@@ -692,7 +731,7 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
     // captured graph is independent of them; per-kernel path: they are baked into the kernel nodes
     if (persistent) DSVC_TRY(build_step_table(h, ha, 0, s));
     if (!h->g_ddpm_valid || (!persistent && (h->g_ddpm_noise != noise || h->g_ddpm_seed != seed))) {
-      DSVC_TRY(capture_graph(h, &h->g_ddpm, [&](cudaStream_t cs) -> int {
+      DSVC_TRY(capture_graph(h, &h->g_ddpm, &h->g_ddpm_nodes, [&](cudaStream_t cs) -> int {
         DSVC_TRY(enqueue_eval(h, ha, cs, 0));
         advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 0);
         DSVC_LAUNCH_CHECK();
@@ -700,9 +739,8 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
       }));
       h->g_ddpm_valid = true; h->g_ddpm_noise = noise; h->g_ddpm_seed = seed;
     }
-    const uint64_t per_step = persistent ? 2ull : 2ull * h->cfg.residual_layers + 4;
     for (int i = 0; i < t_start; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm, s));
-    g_launches.fetch_add(per_step * (uint64_t)t_start, std::memory_order_relaxed);
+    g_launches.fetch_add(h->g_ddpm_nodes * (uint64_t)t_start, std::memory_order_relaxed);
   }
   return store_x(h, x, s);
 }
@@ -732,7 +770,7 @@ int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t inter
       const bool persistent = step_eligible(h);
       if (persistent) DSVC_TRY(build_step_table(h, c, 0, s));   // slot 0 held the FIRST-eval table until here
       if (!h->g_plms_valid) {
-        DSVC_TRY(capture_graph(h, &h->g_plms, [&](cudaStream_t cs) -> int {
+        DSVC_TRY(capture_graph(h, &h->g_plms, &h->g_plms_nodes, [&](cudaStream_t cs) -> int {
           DSVC_TRY(enqueue_eval(h, c, cs, 0));
           advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 1);
           DSVC_LAUNCH_CHECK();
@@ -741,7 +779,7 @@ int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t inter
         h->g_plms_valid = true;
       }
       for (int i = 1; i < n_iter; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_plms, s));
-      g_launches.fetch_add((persistent ? 2ull : 2ull * h->cfg.residual_layers + 4) * (uint64_t)(n_iter - 1), std::memory_order_relaxed);
+      g_launches.fetch_add(h->g_plms_nodes * (uint64_t)(n_iter - 1), std::memory_order_relaxed);
     }
   }
   return store_x(h, x, s);

@@ -144,7 +144,8 @@ int dsvc_cond_encode(const float* hubert, const int64_t* mel2ph, const float* f0
 
 /* Measurement hook (bench.py roofline): enqueue `iters` back-to-back launches of one kernel of the
  * WaveNet layer `layer` on the prepared workspace.  part 0 = dilated conv + conditioner + gate
- * (net.py:69-77), part 1 = output projection + residual + skip (net.py:79-84).  The workspace
+ * (net.py:69-77), part 1 = output projection + residual + skip (net.py:79-84), part 2 = both as the
+ * one fused layer kernel (opt-in DSVC_FUSED_LAYER; DSVC_ESTATE when that mode is not active).  The workspace
  * contents afterwards are unspecified (call prepare / a sampler again before trusting results). */
 int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream);
 

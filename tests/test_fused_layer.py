@@ -1,0 +1,90 @@
+"""The fused WaveNet-layer kernel (csrc/tc_layer.cuh, opt-in DSVC_FUSED_LAYER=1): conv + gate and the output projection
+of one residual layer (net.py:66-84) in ONE launch, a cluster of 2C/64 CTAs per 128-frame tile with a cluster barrier
+between the two contractions.  Same MMAs in the same order and the same epilogue functors as the two separate kernels
+=> the results must be BIT-identical to the default path; parity of that path against the oracle / the reference
+goldens is tests/test_gpu_parity.py.
+
+Run with DSVC_TEST_EXPERIMENTS=1 (the kernel is an experiment until measured on a B200 -- DESIGN.md section 10)."""
+import os
+
+import pytest
+import torch
+
+from oracle import diffsvc_oracle as O
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DSVC_TEST_EXPERIMENTS") != "1", reason="opt-in experiment: set DSVC_TEST_EXPERIMENTS=1")]
+DEV = "cuda"
+
+
+def _model(K_step=1000):
+    import diffsvc_b200 as D
+    from diffsvc_b200.hparams import hparams, DEFAULTS_44K
+    hparams.clear(); hparams.update(DEFAULTS_44K); hparams["pndm_speedup"] = 1
+    sd = O.synth_diffnet_weights(seed=1234)
+    dn = D.DiffNet(128, math_mode="tc3f16")
+    dn.load_state_dict(sd, strict=True)
+    return D.GaussianDiffusion(None, 128, dn, timesteps=1000, K_step=K_step, loss_type="l2", spec_min=[-5.0], spec_max=[0.0]).to(DEV).eval()
+
+
+def _inputs(B, T, steps, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, 256, T, generator=g) * 0.5, torch.randn(B, 1, 128, T, generator=g),
+            torch.randn(steps, B, 1, 128, T, generator=g))
+
+
+def _launches():
+    from diffsvc_b200 import _lib
+    return _lib.load().dsvc_launch_count()
+
+
+def _pair(monkeypatch, fn):
+    """fn(model) on a default handle and on a fused-layer handle; returns (default, fused, launches default, fused)."""
+    monkeypatch.delenv("DSVC_FUSED_LAYER", raising=False)
+    gd0 = _model()
+    l0 = _launches(); a = fn(gd0); la = _launches() - l0
+    monkeypatch.setenv("DSVC_FUSED_LAYER", "2")          # 2: regardless of the grid size
+    gd1 = _model()
+    l0 = _launches(); b = fn(gd1); lb = _launches() - l0
+    return a, b, la, lb
+
+
+@pytest.mark.parametrize("B,T,lens", [(1, 862, None), (1, 43, None), (3, 150, [150, 97, 33]), (2, 1000, None)])
+def test_ddpm_bit_identical_and_fewer_launches(monkeypatch, B, T, lens):
+    steps = 6
+    cond, x0, noise = _inputs(B, T, steps)
+    run = lambda gd: gd.sample(x0.to(DEV), cond.to(DEV), steps, None, noise.to(DEV), lengths=lens).cpu()
+    a, b, la, lb = _pair(monkeypatch, run)
+    if lb >= la:
+        pytest.skip("a cluster of 12 CTAs x 193 KB is not schedulable on this device: the library fell back (launches %d vs %d)" % (lb, la))
+    assert la - lb == steps * 20, (la, lb)             # one kernel less per layer per step
+    assert torch.isfinite(b).all()
+    assert torch.equal(a, b)
+
+
+def test_plms_and_single_eval_bit_identical(monkeypatch):
+    cond, x0, _ = _inputs(1, 300, 1, seed=9)
+
+    def run(gd):
+        eps = gd.denoise_fn(x0.to(DEV), torch.tensor([37], device=DEV), cond.to(DEV)).cpu()
+        x = gd.sample(x0.to(DEV), cond.to(DEV), 1000, 100).cpu()
+        return torch.cat([eps.flatten(), x.flatten()])
+    a, b, la, lb = _pair(monkeypatch, run)
+    if lb >= la:
+        pytest.skip("fused-layer cluster not schedulable on this device")
+    assert torch.equal(a, b)
+
+
+def test_deterministic_and_reusable_across_shapes(monkeypatch):
+    """One handle, several (B, T): the TMA descriptors and the ping-pong planes follow the workspace."""
+    monkeypatch.setenv("DSVC_FUSED_LAYER", "2")
+    gd = _model()
+    outs = []
+    for (B, T) in ((1, 200), (2, 129), (1, 200)):
+        cond, x0, noise = _inputs(B, T, 4, seed=3)
+        outs.append(gd.sample(x0.to(DEV), cond.to(DEV), 4, None, noise.to(DEV)).cpu())
+    assert torch.equal(outs[0], outs[2])
+    monkeypatch.delenv("DSVC_FUSED_LAYER")
+    gd0 = _model()
+    cond, x0, noise = _inputs(2, 129, 4, seed=3)
+    assert torch.equal(outs[1], gd0.sample(x0.to(DEV), cond.to(DEV), 4, None, noise.to(DEV)).cpu())
