@@ -367,7 +367,8 @@ static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s, c
 // and the output projection.
 static int enqueue_layer_fused(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
   const int dil = 1 << (l % h->cfg.dilation_cycle_length);
-  return tc_layer_launch(h->maps.dil[l], h->maps.out[l], mk_gate(h, l), mk_outproj(h, l, tsel), h->B, h->Tmax,
+  const TcGemmMaps* next = l + 1 < h->cfg.residual_layers ? &h->maps.dil[l + 1] : nullptr;
+  return tc_layer_launch(h->maps.dil[l], h->maps.out[l], next, mk_gate(h, l), mk_outproj(h, l, tsel), h->B, h->Tmax,
                          h->cfg.residual_channels, dil, h->passes, s);
 }
 

@@ -36,7 +36,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,    // conv weights, box {64, 32}
                 const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,    // gated activation planes
                 const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,    // out-proj weights, box {64, 32}
-                const EpiGate::Params eg, const EpiOutProj::Params eo, int T, int K, int N, int dil, int passes) {
+                const __grid_constant__ CUtensorMap tmNh, const __grid_constant__ CUtensorMap tmNl,    // NEXT layer's conv weights (L2 prefetch)
+                const EpiGate::Params eg, const EpiOutProj::Params eo, int T, int K, int N, int dil, int passes, int prefetch_next) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   constexpr int BN = LY_BN;
   using Cfg = TcCfg<BN>;
@@ -64,6 +65,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
   const uint32_t tx_bytes = three ? Cfg::STAGE : Cfg::STAGE / 2;
 
   if (warp == 0 && lane == 0) {
+    if (prefetch_next) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmNh) : "memory");
+      if (three) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmNl) : "memory");
+    }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZh) : "memory");
@@ -221,6 +226,22 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       }
       __syncwarp();
     }
+    // The next layer's kernel cannot pre-launch next to this one (its 12-CTA clusters need the SMs this grid holds), so
+    // its weight tiles are not requested early by its own prologue: pull the tiles CTA (.., ny, ..) of that kernel will
+    // read (same ny, all taps and K-blocks) into L2 from here, behind this kernel's own loads.
+    if (prefetch_next && elect_one_sync()) {
+      for (int it = 0; it < total_a; ++it) {
+        const int tap = it / kblocks, kb = it - tap * kblocks;
+        const int r0 = tap * N + (ny >> 1) * 128 + (ny & 1) * 32;
+        tma_prefetch_2d(&tmNh, kb * TC_BK, r0);
+        tma_prefetch_2d(&tmNh, kb * TC_BK, r0 + 64);
+        if (three) {
+          tma_prefetch_2d(&tmNl, kb * TC_BK, r0);
+          tma_prefetch_2d(&tmNl, kb * TC_BK, r0 + 64);
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     for (int it = 0; it < total_b; ++it) {
       const int g = total_a + it;
@@ -300,8 +321,13 @@ inline int tc_layer_probe(int nt, int* usable) {
 }
 
 // one launch = one residual layer; the caller has checked tc_layer_shape_ok() and tc_layer_probe()
-inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const EpiGate::Params& eg, const EpiOutProj::Params& eo,
-                           int B, int T, int C, int dil, int passes, cudaStream_t s) {
+// `mnext`: the next layer's conv-weight maps for the L2 prefetch (null: last layer / prefetch off)
+inline bool tc_layer_prefetch_next() {
+  const char* e = getenv("DSVC_FUSED_PREFETCH");     // default on; 0 switches the next-layer weight prefetch off
+  return !(e && e[0] == '0');
+}
+inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const TcGemmMaps* mnext, const EpiGate::Params& eg,
+                           const EpiOutProj::Params& eo, int B, int T, int C, int dil, int passes, cudaStream_t s) {
   const int N = 2 * C, nt = N / LY_BN;
   DSVC_REQUIRE(nt >= 1 && nt <= 16 && N % 128 == 0 && C % TC_BK == 0, "tc_layer_launch: C=%d does not tile into a cluster", C);
   cudaLaunchConfig_t cfg{};
@@ -323,8 +349,10 @@ inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const Epi
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  const bool pf = mnext != nullptr && tc_layer_prefetch_next();
+  const TcGemmMaps& mn = pf ? *mnext : md;
   DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_layer_kernel, md.a_hi, md.a_lo, md.b32_hi, md.b32_lo, mo.a_hi, mo.a_lo, mo.b32_hi, mo.b32_lo,
-                               eg, eo, T, C, N, dil, passes));
+                               mn.b32_hi, mn.b32_lo, eg, eo, T, C, N, dil, passes, pf ? 1 : 0));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }
