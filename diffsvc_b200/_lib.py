@@ -31,21 +31,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into diffsvc_b200/lib/libdsvc.so (nvcc cross-compiles without a GPU)."""
-    if not force and not _stale():
-        return LIB_PATH
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile csrc/*.cu for sm_100a into diffsvc_b200/lib/libdsvc.so (nvcc cross-compiles without a GPU).
+    `extra_flags` / `out`: developer variants (e.g. -DDSVC_TIMELINE) next to the product library, loaded via DSVC_LIB."""
+    if out is None:
+        out = LIB_PATH
+        if not force and not _stale():
+            return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = out + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise DsvcError("nvcc failed:\n" + r.stdout + r.stderr)
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, out)
+    return out
 
 
 class DiffnetConfig(C.Structure):

@@ -118,7 +118,7 @@ struct dsvc_diffnet {
   PlaneBuf Y, Z, SP, R, XIN;
   PlaneBuf Y2;           // fused-layer mode (tc_layer.cuh): conv-input plane of the odd layers (Y holds the even ones)
   bool pingpong = false; // Y / Y2 alternate by layer parity: a layer's out-proj never overwrites the plane its conv reads
-  int fused_usable = 0;  // 1: a cluster of 2C/64 CTAs of tc_layer_kernel is schedulable on this device (probed in prepare)
+  int fused_usable = 0;  // how many clusters of 2C/64 CTAs of tc_layer_kernel fit the device at once (probed in prepare; 0: none)
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
   // persistent single-launch evaluation (tc_step.cuh): phase tables (host staging + device), grid barrier
   std::vector<StepPhase> step_host[2];
@@ -373,8 +373,10 @@ static int enqueue_layer_fused(dsvc_diffnet* h, int l, int tsel, cudaStream_t s)
 }
 
 static bool fused_layers(const dsvc_diffnet* h) {
-  return h->tc && h->pingpong && h->fused_usable == 1 && !tc_use_halo() &&
-         tc_layer_shape_ok(h->B, h->Tmax, h->cfg.residual_channels);
+  if (!(h->tc && h->pingpong && h->fused_usable >= 1 && !tc_use_halo() &&
+        tc_layer_shape_ok(h->B, h->Tmax, h->cfg.residual_channels))) return false;
+  // automatic mode: only while every frame tile's cluster is resident at once (a second wave of clusters doubles the layer)
+  return tc_layer_env() >= 2 || (long long)ceil_div(h->Tmax, TC_BM) * h->B <= h->fused_usable;
 }
 
 // ---- persistent single-launch evaluation (tc_step.cuh) -----------------------------------------
@@ -703,14 +705,25 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
   }
 #ifdef DSVC_TIMELINE
   if (h->tc) {
-    static long long host_tl[1024][8];
+    static long long host_tl[1024][16];
     DSVC_CUDA(cudaStreamSynchronize(s));
     DSVC_CUDA(cudaMemcpyFromSymbol(host_tl, g_timeline, sizeof(host_tl)));
     const int nct = ceil_div(h->Tmax, TC_BM) * ceil_div(2 * h->cfg.residual_channels, 64) * h->B;
+    if (part == 2) {
+      printf("timeline fused layer (cycles since CTA entry): setup | A:first-operands | A:mma-issued | A:epi-prefetch | A:acc-ready | "
+             "A:staged | A:epi-done | fences | cluster-barrier | B:first-operands | B:mma-issued | B:epi-prefetch | B:acc-ready | "
+             "B:staged | B:epi-done\n");
+      for (int c = 0; c < nct && c < 1024; c += (nct > 12 ? nct / 12 : 1))
+        printf("  cta %3d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c,
+               host_tl[c][0], host_tl[c][1], host_tl[c][2], host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6], host_tl[c][7],
+               host_tl[c][8], host_tl[c][9], host_tl[c][10], host_tl[c][11], host_tl[c][12], host_tl[c][13], host_tl[c][14]);
+    } else {
     printf("timeline part %d (cycles since CTA entry): setup | first-operands | mma-issued | epi-prefetch | acc-ready | staged | epi-done\n", part);
     for (int c = 0; c < nct && c < 1024; c += (nct > 12 ? nct / 12 : 1))
       printf("  cta %3d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, host_tl[c][0], host_tl[c][1], host_tl[c][2],
              host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6]);
+    }
+    fflush(stdout);
   }
 #endif
   return DSVC_OK;

@@ -277,7 +277,7 @@ template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, flo
 
 // ---- optional per-CTA timeline (cycles since kernel entry), build with -DDSVC_TIMELINE ----------
 #ifdef DSVC_TIMELINE
-__device__ long long g_timeline[1024][8];
+__device__ long long g_timeline[1024][16];
 #define TL_MARK(slot) do { if (lane == 0) g_timeline[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 1023][slot] = clock64() - tl0; } while (0)
 #else
 #define TL_MARK(slot) do { } while (0)
@@ -289,9 +289,13 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
                                             uint32_t tmem_base, uint32_t tmem_full_bar, uint32_t tmem_parity, int T, int N,
                                             int m0, int ny, int b, int warp, int lane, bool two_acc
 #ifdef DSVC_TIMELINE
-                                            , long long tl0
+                                            , long long tl0, int tl_off = 0
 #endif
 ) {
+#ifndef DSVC_TIMELINE
+    constexpr int tl_off = 0;
+    (void)tl_off;
+#endif
     // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
     // tcgen05.ld hands each thread one accumulator ROW (a frame); a warp may only touch the TMEM lane
     // quarter (warp % 4).  Global tensors are channels-last, so the four warps of a quarter stage their
@@ -329,9 +333,31 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       cc[h] = EpiCol{};
       if (col_ok) cc[h] = Epi::col(ep, ncol);
     }
-    if (warp == 4) TL_MARK(3);             // epilogue prefetch issued
+    // DSVC_EPI_HOIST (experiment): the per-row inputs (they were all written by EARLIER kernels) are loaded into
+    // registers while the MMAs still run, instead of after the accumulator has been staged: their L2 latency leaves
+    // the epilogue's critical path.  Only for the narrow tiles (<= 4 row iterations per thread: <= 32 registers).
+#ifdef DSVC_EPI_HOIST
+    constexpr bool kHoist = (NH * NIT <= 4);
+#else
+    constexpr bool kHoist = false;
+#endif
+    EpiPre hpre[kHoist ? NH * NIT : 1];
+    if constexpr (kHoist) {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const int ncol = col_of(h);
+        const bool col_ok = Epi::kPair ? true : (ncol < N);
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int p = m0 + row0 + i * RPI + rsub;
+          hpre[h * NIT + i] = EpiPre{};
+          if (p < T && col_ok) hpre[h * NIT + i] = Epi::pre(ep, b, p, ncol);
+        }
+      }
+    }
+    if (warp == 4) TL_MARK(3 + tl_off);    // epilogue prefetch issued
     mbar_wait(tmem_full_bar, tmem_parity);
-    if (warp == 4) TL_MARK(4);             // accumulator ready
+    if (warp == 4) TL_MARK(4 + tl_off);    // accumulator ready
     tc_fence_after();
     constexpr int STG_LD = BN + 4;               // padded row: conflict-free float4 writes
     float* slab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (size_t)q * 32 * STG_LD;
@@ -354,7 +380,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       }
     }
     asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
-    if (warp == 4) TL_MARK(5);             // staged to smem
+    if (warp == 4) TL_MARK(5 + tl_off);    // staged to smem
     const float* stg = slab + (size_t)(cg * 8) * STG_LD;
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
@@ -365,7 +391,8 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
         const int p = m0 + row0 + i * RPI + rsub;
-        if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
+        if constexpr (kHoist) pre[i] = hpre[h * NIT + i];
+        else if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
       }
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {

@@ -37,7 +37,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,    // gated activation planes
                 const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,    // out-proj weights, box {64, 32}
                 const __grid_constant__ CUtensorMap tmNh, const __grid_constant__ CUtensorMap tmNl,    // NEXT layer's conv weights (L2 prefetch)
-                const EpiGate::Params eg, const EpiOutProj::Params eo, int T, int K, int N, int dil, int passes, int prefetch_next) {
+                const EpiGate::Params eg, const EpiOutProj::Params eo, int T, int K, int N, int dil, int passes, int prefetch_next, int light_fence) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   constexpr int BN = LY_BN;
   using Cfg = TcCfg<BN>;
@@ -97,6 +97,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (warp == 3) TL_MARK(0);   // setup done
 
   // ---- operand loads ---------------------------------------------------------------------------
   // phase A weights: pair tiles live in a 128-row super-tile packed [64 gate rows | 64 filter rows]; CTA ny takes gate
@@ -188,6 +189,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
+      if (it == 0) TL_MARK(1);             // first operands of phase A landed
       tc_fence_after();
       if (elect_one_sync()) {
         issue_stage(s, it == 0);
@@ -196,6 +198,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       }
       __syncwarp();
     }
+    TL_MARK(2);                            // phase A MMAs issued
   }
   pdl_wait();   // every warp: the epilogues read and overwrite tensors of the previous kernel
 #ifdef DSVC_TIMELINE
@@ -205,12 +208,17 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
 #endif
 
   // ============ Z of this frame tile is complete once every CTA of the cluster has passed here ============
-  __threadfence();                                      // this thread's Z stores are performed device-wide ...
+  if (warp == 4) TL_MARK(6);                            // epilogue A done
+  // light_fence (DSVC_FUSED_FENCE=0): rely on the cluster barrier's own release / acquire for the visibility of the
+  // Z stores and keep only the proxy fences; default: a device-scope fence per thread first
+  if (!light_fence) __threadfence();                    // this thread's Z stores are performed device-wide ...
   asm volatile("fence.proxy.async;" ::: "memory");      // ... and ordered against the peers' TMA (async-proxy) reads
+  if (warp == 4) TL_MARK(7);                            // fences done
   tc_fence_before();                                    // TMEM reads of phase A precede phase B's MMAs
   __syncwarp();
   cluster_sync_all();                                   // also: every warp is done with the staging slab (smem ring)
   tc_fence_after();
+  if (warp == 4) TL_MARK(8);                            // cluster barrier passed
 
   // =================================== phase B: output projection ===================================
   if (warp == 0) {
@@ -248,6 +256,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       const int s = g % STAGES;
       const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
+      if (it == 0) TL_MARK(9);             // first operands of phase B landed
       tc_fence_after();
       if (elect_one_sync()) {
         issue_stage(s, it == 0);
@@ -256,9 +265,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       }
       __syncwarp();
     }
+    TL_MARK(10);                           // phase B MMAs issued
   }
 #ifdef DSVC_TIMELINE
-  tc_epilogue<EpiOutProj, BN>(eo, smem_raw, smem_base, tmem_base, tmem_full_bar, 1u, T, N, m0, ny, b, warp, lane, three, tl0);
+  tc_epilogue<EpiOutProj, BN>(eo, smem_raw, smem_base, tmem_base, tmem_full_bar, 1u, T, N, m0, ny, b, warp, lane, three, tl0, 8);
+  if (warp == 4) TL_MARK(14);              // epilogue B done
 #else
   tc_epilogue<EpiOutProj, BN>(eo, smem_raw, smem_base, tmem_base, tmem_full_bar, 1u, T, N, m0, ny, b, warp, lane, three);
 #endif
@@ -292,7 +303,7 @@ inline bool tc_layer_shape_ok(int B, int T, int C) {
 // Can a cluster of nt = 2C/64 CTAs of this kernel (193 KB of shared memory each) be co-scheduled on the current device?
 // Sets the function attributes on first use; cached per cluster size.  Called from dsvc_diffnet_prepare (outside any
 // stream capture).  *usable = 0: the caller keeps the two separate kernels.
-inline int tc_layer_probe(int nt, int* usable) {
+inline int tc_layer_probe(int nt, int* usable) {   // *usable = max co-resident clusters (0: not schedulable)
   static int cache[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
   *usable = 0;
   if (nt < 1 || nt > 16) return DSVC_OK;
@@ -314,7 +325,7 @@ inline int tc_layer_probe(int nt, int* usable) {
     int clusters = 0;
     const cudaError_t e = cudaOccupancyMaxActiveClusters(&clusters, kern, &q);
     if (e != cudaSuccess) cudaGetLastError();
-    cache[nt] = (e == cudaSuccess && clusters >= 1) ? 1 : 0;
+    cache[nt] = (e == cudaSuccess && clusters >= 1) ? clusters : 0;
   }
   *usable = cache[nt];
   return DSVC_OK;
@@ -325,6 +336,10 @@ inline int tc_layer_probe(int nt, int* usable) {
 inline bool tc_layer_prefetch_next() {
   const char* e = getenv("DSVC_FUSED_PREFETCH");     // default on; 0 switches the next-layer weight prefetch off
   return !(e && e[0] == '0');
+}
+inline bool tc_layer_light_fence() {
+  const char* e = getenv("DSVC_FUSED_FENCE");        // default: device-scope fence per thread; 0: proxy fences + barrier only
+  return e && e[0] == '0';
 }
 inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const TcGemmMaps* mnext, const EpiGate::Params& eg,
                            const EpiOutProj::Params& eo, int B, int T, int C, int dil, int passes, cudaStream_t s) {
@@ -352,7 +367,7 @@ inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const TcG
   const bool pf = mnext != nullptr && tc_layer_prefetch_next();
   const TcGemmMaps& mn = pf ? *mnext : md;
   DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_layer_kernel, md.a_hi, md.a_lo, md.b32_hi, md.b32_lo, mo.a_hi, mo.a_lo, mo.b32_hi, mo.b32_lo,
-                               mn.b32_hi, mn.b32_lo, eg, eo, T, C, N, dil, passes, pf ? 1 : 0));
+                               mn.b32_hi, mn.b32_lo, eg, eo, T, C, N, dil, passes, pf ? 1 : 0, tc_layer_light_fence() ? 1 : 0));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }

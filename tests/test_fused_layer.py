@@ -41,6 +41,7 @@ def _launches():
 def _pair(monkeypatch, fn):
     """fn(model) on a default handle and on a fused-layer handle; returns (default, fused, launches default, fused)."""
     monkeypatch.delenv("DSVC_FUSED_LAYER", raising=False)
+    monkeypatch.setenv("DSVC_SPLITK", "0")               # the split-K conv (automatic for short clips) sums in another order
     gd0 = _model()
     l0 = _launches(); a = fn(gd0); la = _launches() - l0
     monkeypatch.setenv("DSVC_FUSED_LAYER", "2")          # 2: regardless of the grid size
@@ -49,8 +50,10 @@ def _pair(monkeypatch, fn):
     return a, b, la, lb
 
 
+@pytest.mark.parametrize("fence", ["1", "0"])
 @pytest.mark.parametrize("B,T,lens", [(1, 862, None), (1, 43, None), (3, 150, [150, 97, 33]), (2, 1000, None)])
-def test_ddpm_bit_identical_and_fewer_launches(monkeypatch, B, T, lens):
+def test_ddpm_bit_identical_and_fewer_launches(monkeypatch, B, T, lens, fence):
+    monkeypatch.setenv("DSVC_FUSED_FENCE", fence)        # 0: proxy fences + cluster barrier only
     steps = 6
     cond, x0, noise = _inputs(B, T, steps)
     run = lambda gd: gd.sample(x0.to(DEV), cond.to(DEV), steps, None, noise.to(DEV), lengths=lens).cpu()
@@ -64,6 +67,7 @@ def test_ddpm_bit_identical_and_fewer_launches(monkeypatch, B, T, lens):
 
 def test_plms_and_single_eval_bit_identical(monkeypatch):
     cond, x0, _ = _inputs(1, 300, 1, seed=9)
+    monkeypatch.delenv("DSVC_FUSED_FENCE", raising=False)
 
     def run(gd):
         eps = gd.denoise_fn(x0.to(DEV), torch.tensor([37], device=DEV), cond.to(DEV)).cpu()

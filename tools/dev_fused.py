@@ -16,7 +16,7 @@ ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
 def model(env):
-    for k in ("DSVC_FUSED_LAYER", "DSVC_FUSED_PREFETCH"):
+    for k in ("DSVC_FUSED_LAYER", "DSVC_FUSED_PREFETCH", "DSVC_FUSED_FENCE", "DSVC_SPLITK"):
         os.environ.pop(k, None)
     os.environ.update(env)
     dn = D.DiffNet(128, math_mode="tc3f16"); dn.load_state_dict(sd)
@@ -47,9 +47,13 @@ def probe(tag, env, B, T, steps):
 
 
 if __name__ == "__main__":
-    for (B, T, steps) in ((1, 862, 60), (1, 43, 100), (2, 689, 30)):
-        ref = probe("default      ", {}, B, T, steps)
-        for tag, env in (("fused+prefetch", {"DSVC_FUSED_LAYER": "2"}), ("fused        ", {"DSVC_FUSED_LAYER": "2", "DSVC_FUSED_PREFETCH": "0"})):
+    print("== lib %s" % os.environ.get("DSVC_LIB", "product"), flush=True)
+    for (B, T, steps) in ((1, 862, 60), (1, 43, 100)):
+        ref = probe("default (no split-K)", {"DSVC_SPLITK": "0"}, B, T, steps)
+        if T == 43:
+            probe("default (split-K)   ", {}, B, T, steps)
+        for tag, env in (("fused               ", {"DSVC_FUSED_LAYER": "2"}),
+                         ("fused, light fence  ", {"DSVC_FUSED_LAYER": "2", "DSVC_FUSED_FENCE": "0"})):
             try:
                 out = probe(tag, env, B, T, steps)
                 print("    bit-identical to default: %s" % bool(torch.equal(out, ref)), flush=True)
