@@ -333,10 +333,12 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       cc[h] = EpiCol{};
       if (col_ok) cc[h] = Epi::col(ep, ncol);
     }
-    // DSVC_EPI_HOIST (experiment): the per-row inputs (they were all written by EARLIER kernels) are loaded into
-    // registers while the MMAs still run, instead of after the accumulator has been staged: their L2 latency leaves
-    // the epilogue's critical path.  Only for the narrow tiles (<= 4 row iterations per thread: <= 32 registers).
-#ifdef DSVC_EPI_HOIST
+    // The per-row inputs (all written by EARLIER kernels: residual stream, skip sum, conditioner slab, sampler state)
+    // are loaded into registers while the MMAs still run, not after the accumulator has been staged: their L2 latency
+    // leaves the epilogue's critical path (measured, one clip: staged -> done 2200 -> 1700 cycles in the conv kernel,
+    // 3100 -> 2400 in the out-projection, 394 -> 384 us per DDPM step; bit-identical results).  Only for the narrow
+    // tiles (<= 4 row iterations per thread: <= 32 registers).  -DDSVC_NO_EPI_HOIST restores the late loads.
+#ifndef DSVC_NO_EPI_HOIST
     constexpr bool kHoist = (NH * NIT <= 4);
 #else
     constexpr bool kHoist = false;

@@ -184,6 +184,23 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
       }
       __syncwarp();
     }
+    // Optional (DSVC_FUSED_PREFETCH=1; measured: no effect on the step time): the next layer's kernel cannot pre-launch
+    // next to this one (its 12-CTA clusters need the SMs this grid holds), so its weight tiles are not requested early by
+    // its own prologue.  Pull the tiles CTA (.., ny, ..) of that kernel will read into L2 from here -- this warp is
+    // idle until the accumulator is complete (issuing them after phase B's loads delayed the epilogue by ~700 cycles).
+    if (prefetch_next && elect_one_sync()) {
+      for (int it = 0; it < total_a; ++it) {
+        const int tap = it / kblocks, kb = it - tap * kblocks;
+        const int r0 = tap * N + (ny >> 1) * 128 + (ny & 1) * 32;
+        tma_prefetch_2d(&tmNh, kb * TC_BK, r0);
+        tma_prefetch_2d(&tmNh, kb * TC_BK, r0 + 64);
+        if (three) {
+          tma_prefetch_2d(&tmNl, kb * TC_BK, r0);
+          tma_prefetch_2d(&tmNl, kb * TC_BK, r0 + 64);
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     for (int it = 0; it < total_a; ++it) {
       const int s = it % STAGES;
@@ -209,8 +226,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
 
   // ============ Z of this frame tile is complete once every CTA of the cluster has passed here ============
   if (warp == 4) TL_MARK(6);                            // epilogue A done
-  // light_fence (DSVC_FUSED_FENCE=0): rely on the cluster barrier's own release / acquire for the visibility of the
-  // Z stores and keep only the proxy fences; default: a device-scope fence per thread first
+  // light_fence (default): rely on the cluster barrier's own release / acquire for the visibility of the Z stores and
+  // keep only the proxy fences; DSVC_FUSED_FENCE=1: a device-scope fence per thread first
   if (!light_fence) __threadfence();                    // this thread's Z stores are performed device-wide ...
   asm volatile("fence.proxy.async;" ::: "memory");      // ... and ordered against the peers' TMA (async-proxy) reads
   if (warp == 4) TL_MARK(7);                            // fences done
@@ -233,21 +250,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant_
         load_b(it, s);
       }
       __syncwarp();
-    }
-    // The next layer's kernel cannot pre-launch next to this one (its 12-CTA clusters need the SMs this grid holds), so
-    // its weight tiles are not requested early by its own prologue: pull the tiles CTA (.., ny, ..) of that kernel will
-    // read (same ny, all taps and K-blocks) into L2 from here, behind this kernel's own loads.
-    if (prefetch_next && elect_one_sync()) {
-      for (int it = 0; it < total_a; ++it) {
-        const int tap = it / kblocks, kb = it - tap * kblocks;
-        const int r0 = tap * N + (ny >> 1) * 128 + (ny & 1) * 32;
-        tma_prefetch_2d(&tmNh, kb * TC_BK, r0);
-        tma_prefetch_2d(&tmNh, kb * TC_BK, r0 + 64);
-        if (three) {
-          tma_prefetch_2d(&tmNl, kb * TC_BK, r0);
-          tma_prefetch_2d(&tmNl, kb * TC_BK, r0 + 64);
-        }
-      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -334,12 +336,14 @@ inline int tc_layer_probe(int nt, int* usable) {   // *usable = max co-resident 
 // one launch = one residual layer; the caller has checked tc_layer_shape_ok() and tc_layer_probe()
 // `mnext`: the next layer's conv-weight maps for the L2 prefetch (null: last layer / prefetch off)
 inline bool tc_layer_prefetch_next() {
-  const char* e = getenv("DSVC_FUSED_PREFETCH");     // default on; 0 switches the next-layer weight prefetch off
-  return !(e && e[0] == '0');
+  const char* e = getenv("DSVC_FUSED_PREFETCH");     // default off (no measured effect); 1 switches the next-layer weight prefetch on
+  return e && e[0] == '1';
 }
 inline bool tc_layer_light_fence() {
-  const char* e = getenv("DSVC_FUSED_FENCE");        // default: device-scope fence per thread; 0: proxy fences + barrier only
-  return e && e[0] == '0';
+  // default: proxy fences + the cluster barrier's release / acquire (bit-identical in every test, ~500 cycles shorter);
+  // DSVC_FUSED_FENCE=1 adds a device-scope fence per thread in front
+  const char* e = getenv("DSVC_FUSED_FENCE");
+  return !(e && e[0] == '1');
 }
 inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const TcGemmMaps* mnext, const EpiGate::Params& eg,
                            const EpiOutProj::Params& eo, int B, int T, int C, int dil, int passes, cudaStream_t s) {

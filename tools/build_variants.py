@@ -1,13 +1,12 @@
 """Developer builds next to the product library (loaded with DSVC_LIB=...):
   libdsvc_tl.so     -DDSVC_TIMELINE                   in-kernel cycle stamps (dsvc_diffnet_run_layer prints them)
-  libdsvc_hoist.so  -DDSVC_EPI_HOIST                  epilogue row inputs loaded before the accumulator wait
-  libdsvc_tlh.so    both"""
+  libdsvc_late.so   -DDSVC_NO_EPI_HOIST               epilogue row inputs loaded after the accumulator wait (the old order)"""
 import os, sys
 from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffsvc_b200 import _lib
 
-V = {"libdsvc_tl.so": ["-DDSVC_TIMELINE"], "libdsvc_hoist.so": ["-DDSVC_EPI_HOIST"], "libdsvc_tlh.so": ["-DDSVC_TIMELINE", "-DDSVC_EPI_HOIST"]}
+V = {"libdsvc_tl.so": ["-DDSVC_TIMELINE"], "libdsvc_late.so": ["-DDSVC_NO_EPI_HOIST"]}
 names = sys.argv[1:] or list(V)
 with ThreadPoolExecutor(len(names)) as ex:
     for r in ex.map(lambda n: _lib.build(force=True, extra_flags=V[n], out=os.path.join(_lib.LIB_DIR, n)), names):

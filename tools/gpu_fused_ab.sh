@@ -8,6 +8,6 @@ echo "timeline rc=$?" > gpurun_out/fused_rc.txt; cat gpurun_out/fused_timeline.l
 echo "ab rc=$?" >> gpurun_out/fused_rc.txt; cat gpurun_out/fused_ab.log
 ( time DSVC_TEST_EXPERIMENTS=1 timeout 240 python -m pytest tests/test_fused_layer.py -x -q ) > gpurun_out/fused_tests.log 2>&1
 echo "fused tests rc=$?" >> gpurun_out/fused_rc.txt; tail -n 6 gpurun_out/fused_tests.log
-( DSVC_LIB=$L/libdsvc_hoist.so timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or chain_full or composition or ragged or nsf" ) > gpurun_out/fused_hoist_subset.log 2>&1
+( DSVC_LIB=$L/libdsvc_hoist.so timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "chain_full or composition or nsf_golden" ) > gpurun_out/fused_hoist_subset.log 2>&1
 echo "hoist subset rc=$?" >> gpurun_out/fused_rc.txt; tail -n 4 gpurun_out/fused_hoist_subset.log
 cat gpurun_out/fused_rc.txt
