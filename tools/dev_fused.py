@@ -53,7 +53,7 @@ if __name__ == "__main__":
         if T == 43:
             probe("default (split-K)   ", {}, B, T, steps)
         for tag, env in (("fused               ", {"DSVC_FUSED_LAYER": "2"}),
-                         ("fused, light fence  ", {"DSVC_FUSED_LAYER": "2", "DSVC_FUSED_FENCE": "0"})):
+                         ("fused, device fence ", {"DSVC_FUSED_LAYER": "2", "DSVC_FUSED_FENCE": "1"})):
             try:
                 out = probe(tag, env, B, T, steps)
                 print("    bit-identical to default: %s" % bool(torch.equal(out, ref)), flush=True)

@@ -21,6 +21,6 @@ h = dn.handle()
 print("== lib %s  T=%d" % (os.environ.get("DSVC_LIB", "product"), T), flush=True)
 for part in (0, 1, 2):
     _lib.check(lib.dsvc_diffnet_run_layer(h, 3, part, 4, _lib.current_stream())); torch.cuda.synchronize()
-os.environ["DSVC_FUSED_FENCE"] = "0"
-print("== fused, light fence (DSVC_FUSED_FENCE=0)", flush=True)
+os.environ["DSVC_FUSED_FENCE"] = "1"
+print("== fused, device-scope fence (DSVC_FUSED_FENCE=1)", flush=True)
 _lib.check(lib.dsvc_diffnet_run_layer(h, 3, 2, 4, _lib.current_stream())); torch.cuda.synchronize()
