@@ -169,8 +169,6 @@ def run_reference(args, rank):
     per_clip = sum(times) / len(times)
     val = audio / per_clip
     line = base_line(args, val, per_clip * 1000.0 * args.batch)
-    line["config"]["l2"] = "n/a (host arm)"
-    line["config"]["parallelism"] = "rank 0 only, %d host threads" % threads
     line.update({"impl": "reference", "dtype": "f32", "gpu_launches": 0,
                  "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": threads, "kind": "port",
                                   "sample": "%d of %d DDPM steps + 1 NSF-HiFiGAN pass of one %d-frame clip per bench step, "
