@@ -14,12 +14,16 @@
 // counter simply runs on through the second phase.  The arithmetic (MMA order, epilogue functors) is the one of the
 // two separate kernels, so results are bit-identical to them.
 //
-// The kernel boundary this removes costs ~3 us per layer on one clip (grid drain + dependent release + prologue),
-// against ~0.5 us for a cluster barrier.  The write-after-read hazard it would otherwise create -- phase B of a fast
-// cluster overwriting the conv-input plane Y while a neighbouring cluster's phase A still reads its +-dil halo rows
-// from it -- is removed by ping-ponging Y between two planes by layer parity (diffnet.cu: `pingpong`).
+// The write-after-read hazard fusion would otherwise create -- phase B of a fast cluster overwriting the conv-input
+// plane Y while a neighbouring cluster's phase A still reads its +-dil halo rows from it -- is removed by ping-ponging
+// Y between two planes by layer parity (diffnet.cu: `pingpong`).
 //
-// Opt-in (DSVC_FUSED_LAYER=1) until measured on a B200: see DESIGN.md section 10.
+// Measured on B200 (profiles/r1f_fused_layer_timeline.txt, r1f_fused_layer_ab.txt; one 862-frame clip): bit-identical;
+// the in-kernel hand-over (last Z store -> first out-proj operands in smem) takes 4370 cycles = proxy fence 1300-1700 +
+// cluster barrier 1400 + TMA from L2 1300, against ~6500 for the PDL kernel boundary it replaces; but the 12-CTA
+// clusters fill 7 of the 8 GPCs, so the next layer's kernel cannot pre-launch next to this one.  Net: 17.9 vs 18.4 us
+// per layer back to back, 381.4 vs 384.1 us per DDPM step -- within noise, hence opt-in (DSVC_FUSED_LAYER=1|2);
+// DESIGN.md section 3.1c.
 #pragma once
 #include "tc_gemm.cuh"
 
