@@ -85,6 +85,21 @@ struct DevBuf {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Raise a kernel's dynamic shared-memory limit.  Function attributes belong to the device (context), so the
+// "already done" note is kept per device: one process may drive several GPUs (handles are created on the weight's device).
+template <auto Kern>
+inline int ensure_dyn_smem(int bytes) {
+  static std::atomic<int> done[64];
+  int dev = 0;
+  DSVC_CUDA(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (!tracked || done[dev].load(std::memory_order_relaxed) < bytes) {
+    DSVC_CUDA(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (tracked) done[dev].store(bytes, std::memory_order_relaxed);
+  }
+  return DSVC_OK;
+}
+
 // ---- device math that must not be contracted into FMAs (bit-faithful to the reference's
 //      separately-rounded tensor ops) -------------------------------------------------------
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }

@@ -4,8 +4,6 @@
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
 #include "tc_gemm.cuh"
-#include "tc_conv3.cuh"
-#include "tc_step.cuh"
 #include "tc_splitk.cuh"
 #include "tc_layer.cuh"
 
@@ -69,7 +67,9 @@ __global__ void cond_encode_kernel(const float* __restrict__ hubert, const long 
   for (int h = threadIdx.x; h < H; h += blockDim.x) orow[h] = live ? add_rn(hrow[h], erow[h]) : 0.0f;
 }
 
-__global__ void set_state_kernel(StepState* st, int t, int interval) {
+__global__ void set_state_kernel(StepState* st, int t, int interval, unsigned long long seed, const float* noise) {
+  st->seed = seed;
+  st->noise = noise;
   st->t = t;
   st->t_prev = max(t - interval, 0);
   st->interval = interval;
@@ -120,20 +120,13 @@ struct dsvc_diffnet {
   bool pingpong = false; // Y / Y2 alternate by layer parity: a layer's out-proj never overwrites the plane its conv reads
   int fused_usable = 0;  // how many clusters of 2C/64 CTAs of tc_layer_kernel fit the device at once (probed in prepare; 0: none)
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
-  // persistent single-launch evaluation (tc_step.cuh): phase tables (host staging + device), grid barrier
-  std::vector<StepPhase> step_host[2];
-  DevBuf step_dev[2], gbar;
-  DevBuf dep_cnt;        // tile-dependency counters [B * m_tiles] (tc_gemm.cuh TcDep)
   DevBuf sk_slab;        // split-K partial tiles [B][m_tiles][n_tiles][3][128][128] fp32 (tc_splitk.cuh)
-  int step_mode[2] = {-1, -1};
   int num_sms = 148;
   // CUDA graphs of one sampler step
   cudaGraphExec_t g_ddpm = nullptr, g_plms = nullptr;
   cudaStream_t cap_stream = nullptr;   // private stream used only to record graphs (the caller's may be the
                                        // legacy default stream, which cannot be captured)
   uint64_t g_ddpm_nodes = 0, g_plms_nodes = 0;   // kernels per replay of each graph
-  const float* g_ddpm_noise = nullptr;
-  unsigned long long g_ddpm_seed = 0;
   bool g_ddpm_valid = false, g_plms_valid = false;
 
   ~dsvc_diffnet() {
@@ -237,10 +230,6 @@ static int tc_build_maps(dsvc_diffnet* h) {
   auto gemm = [&](TcGemmMaps& g, const PlaneBuf& a, int K, const F16Pair& w, int rows) -> int {
     DSVC_TRY(tc_make_a_map(&g.a_hi, a.hi.as<__half>(), B, T, K));
     DSVC_TRY(tc_make_a_map(&g.a_lo, a.lo.as<__half>(), B, T, K));
-    DSVC_TRY(tc_make_a_map(&g.a64_hi, a.hi.as<__half>(), B, T, K, 64));
-    DSVC_TRY(tc_make_a_map(&g.a64_lo, a.lo.as<__half>(), B, T, K, 64));
-    DSVC_TRY(tc_make_a_map(&g.a32_hi, a.hi.as<__half>(), B, T, K, 32));
-    DSVC_TRY(tc_make_a_map(&g.a32_lo, a.lo.as<__half>(), B, T, K, 32));
     DSVC_TRY(tc_make_b_map(&g.b_hi, w.hi.as<__half>(), rows, K, 128));
     DSVC_TRY(tc_make_b_map(&g.b_lo, w.lo.as<__half>(), rows, K, 128));
     DSVC_TRY(tc_make_b_map(&g.b32_hi, w.hi.as<__half>(), rows, K, 32));
@@ -257,8 +246,6 @@ static int tc_build_maps(dsvc_diffnet* h) {
   for (int l = 0; l < L; ++l) {
     const PlaneBuf& yin = (h->pingpong && (l & 1)) ? h->Y2 : h->Y;
     DSVC_TRY(gemm(h->maps.dil[l], yin, C, *h->h_dil[l], 3 * 2 * C));
-    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_hi, yin.hi.as<__half>(), B, T, C));
-    DSVC_TRY(tc3_make_a_map(&h->maps.dil[l].a144_lo, yin.lo.as<__half>(), B, T, C));
     DSVC_TRY(gemm(h->maps.out[l], h->Z, C, *h->h_out[l], 2 * C));
   }
   return DSVC_OK;
@@ -268,10 +255,7 @@ static int tc_build_maps(dsvc_diffnet* h) {
 struct HeadArgs {
   int mode = HEAD_EVAL;
   float* out = nullptr;
-  const float* noise = nullptr;
-  unsigned long long seed = 0;
   int tsel = 0;   // 0: step table row st->t, 1: st->t_prev (second eval of the first PLMS iteration)
-  int dep_evals_before = 0;   // evaluations already counted in the tile-dependency counters when st->step == 0
 };
 
 static ConvGemmParams base_params(const float* A, const float* W, int B, int T, int Cin, int Cout, int taps, int dil) {
@@ -326,39 +310,34 @@ static EpiHead::Params mk_head(const dsvc_diffnet* h, const HeadArgs& ha) {
   e.bias = h->b_head.as<float>(); e.st = h->state.as<StepState>(); e.mode = ha.mode; e.B = h->B; e.Tmax = h->Tmax;
   e.M = h->cfg.mel_bins; e.out = ha.out; e.xs = h->XS.as<float>(); e.XIN = h->XIN.view(h->tc);
   e.c_recip = h->c_recip.as<float>(); e.c_recipm1 = h->c_recipm1.as<float>(); e.c_coef1 = h->c_coef1.as<float>();
-  e.c_coef2 = h->c_coef2.as<float>(); e.c_logvar = h->c_logvar.as<float>(); e.noise = ha.noise; e.seed = ha.seed;
+  e.c_coef2 = h->c_coef2.as<float>(); e.c_logvar = h->c_logvar.as<float>();
   e.alphas_cumprod = h->c_acp.as<float>(); e.hist = h->hist.as<float>();
   e.wscale = h->tc ? h->h_head.inv_scale : 1.f;
   return e;
 }
 
 // K3a: dilated conv + hoisted conditioner + gate -> Z
-static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
+static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
   const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
   const int dil = 1 << (l % h->cfg.dilation_cycle_length);
   const EpiGate::Params e = mk_gate(h, l);
   if (h->tc) {
     const TcGemmMaps& m = h->maps.dil[l];
-    if (tc_use_halo() && dil <= TC3_HALO) {   // one activation tile per K-block shared by the three taps
-      if (tc_narrow_tiles(B, T, 2 * C))
-        return tc3_launch_bn<EpiGate, 64>(m.a144_hi, m.a144_lo, m.b32_hi, m.b32_lo, e, B, T, C, 2 * C, dil, h->passes, s);
-      return tc3_launch_bn<EpiGate, 128>(m.a144_hi, m.a144_lo, m.b_hi, m.b_lo, e, B, T, C, 2 * C, dil, h->passes, s);
-    }
     // grids that leave SMs idle (one clip): one tap per CTA in a 3-CTA cluster, reduced through an L2 slab
-    if (h->passes == 3 && dep.cnt == nullptr && h->sk_slab.bytes >= tc_splitk_slab_bytes(B, T, 2 * C) &&
+    if (h->passes == 3 && h->sk_slab.bytes >= tc_splitk_slab_bytes(B, T, 2 * C) &&
         tc_splitk_eligible(B, T, 2 * C, 3, h->num_sms))
       return tc_splitk_launch<EpiGate>(m, e, h->sk_slab.as<float>(), B, T, C, 2 * C, dil, s);
-    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s, dep);
+    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s);
   }
   const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;
   return launch_fp32<EpiGate>(h, base_params(h->Y.f32.as<float>(), W, B, T, C, 2 * C, 3, dil), e, s);
 }
 
 // K3b: output projection + residual + skip
-static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
+static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
   const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
   const EpiOutProj::Params e = mk_outproj(h, l, tsel);
-  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s, dep);
+  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s);
   const float* W = h->w_out.as<float>() + (size_t)l * 2 * C * C;
   return launch_fp32<EpiOutProj>(h, base_params(h->Z.f32.as<float>(), W, B, T, C, 2 * C, 1, 0), e, s);
 }
@@ -373,135 +352,39 @@ static int enqueue_layer_fused(dsvc_diffnet* h, int l, int tsel, cudaStream_t s)
 }
 
 static bool fused_layers(const dsvc_diffnet* h) {
-  if (!(h->tc && h->pingpong && h->fused_usable >= 1 && !tc_use_halo() &&
+  if (!(h->tc && h->pingpong && h->fused_usable >= 1 &&
         tc_layer_shape_ok(h->B, h->Tmax, h->cfg.residual_channels))) return false;
   // automatic mode: only while every frame tile's cluster is resident at once (a second wave of clusters doubles the layer)
   return tc_layer_env() >= 2 || (long long)ceil_div(h->Tmax, TC_BM) * h->B <= h->fused_usable;
 }
 
-// ---- persistent single-launch evaluation (tc_step.cuh) -----------------------------------------
-static bool step_eligible(const dsvc_diffnet* h) {
-  static int env = -1;
-  // opt-in: correct (all parity tests pass) but measured SLOWER than 43 PDL-chained launches on B200
-  // (597 vs 407 us per DDPM step for one 862-frame clip): a global-memory grid barrier costs about as
-  // much as a PDL kernel boundary and the per-kernel path overlaps its prologue + first weight tiles
-  // with the previous kernel's tail.  Kept as a documented experiment.
-  if (env < 0) { const char* e = getenv("DSVC_PERSISTENT"); env = (e && e[0] == '1') ? 1 : 0; }
-  if (!env || !h->tc) return false;
-  const int C = h->cfg.residual_channels, M = h->cfg.mel_bins;
-  if ((2 * C) % 64 || C % 64 || M % 64) return false;
-  const long long tiles = (long long)ceil_div(h->Tmax, TC_BM) * h->B * ((2 * C) / STEP_BN);
-  return tiles <= h->num_sms;
-}
-
-// table slot: 0 = tsel 0 evaluations (eval / DDPM / PLMS first + next), 1 = PLMS second (tsel 1)
-static int build_step_table(dsvc_diffnet* h, const HeadArgs& ha, int slot, cudaStream_t s) {
-  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
-  const int B = h->B, T = h->Tmax, mt = ceil_div(T, TC_BM);
-  std::vector<StepPhase>& tab = h->step_host[slot];
-  tab.resize(2 * L + 3);
-  auto fill = [&](StepPhase& ph, const TcGemmMaps& m, int type, int K, int N, int taps, int dil) {
-    memset(&ph, 0, sizeof(ph));
-    ph.a_hi = m.a_hi; ph.a_lo = m.a_lo; ph.b_hi = m.b32_hi; ph.b_lo = m.b32_lo;
-    ph.type = type; ph.K = K; ph.N = N; ph.taps = taps; ph.dil = dil;
-    ph.m_tiles = mt; ph.n_tiles = N / STEP_BN; ph.tiles = B * mt * ph.n_tiles;
-  };
-  int p = 0;
-  fill(tab[p], h->maps.in, PH_INPROJ, M, C, 1, 0); tab[p].ep.inproj = mk_inproj(h, ha.tsel); ++p;
-  for (int l = 0; l < L; ++l) {
-    const int dil = 1 << (l % h->cfg.dilation_cycle_length);
-    fill(tab[p], h->maps.dil[l], PH_GATE, C, 2 * C, 3, dil); tab[p].ep.gate = mk_gate(h, l); ++p;
-    fill(tab[p], h->maps.out[l], PH_OUTPROJ, C, 2 * C, 1, 0); tab[p].ep.outproj = mk_outproj(h, l, ha.tsel); ++p;
-  }
-  fill(tab[p], h->maps.skip, PH_SKIPPROJ, C, C, 1, 0); tab[p].ep.skip = mk_skip(h); ++p;
-  fill(tab[p], h->maps.head, PH_HEAD, C, M, 1, 0); tab[p].ep.head = mk_head(h, ha); ++p;
-  DSVC_TRY(h->step_dev[slot].reserve(tab.size() * sizeof(StepPhase)));
-  DSVC_CUDA(cudaMemcpyAsync(h->step_dev[slot].p, tab.data(), tab.size() * sizeof(StepPhase), cudaMemcpyHostToDevice, s));
-  h->step_mode[slot] = ha.mode;
-  return DSVC_OK;
-}
-
-static int launch_step(dsvc_diffnet* h, int slot, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSVC_CUDA(cudaFuncSetAttribute(tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<STEP_BN>::SMEM));
-    attr_set = true;
-  }
-  const int C = h->cfg.residual_channels;
-  const int grid = ceil_div(h->Tmax, TC_BM) * h->B * ((2 * C) / STEP_BN);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<STEP_BN>::SMEM;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the phases are separated by a grid barrier
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const StepPhase* tab = h->step_dev[slot].as<StepPhase>();
-  const int nph = 2 * h->cfg.residual_layers + 3;
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_step_kernel, tab, nph, h->Tmax, h->passes, h->gbar.as<unsigned>()));
-  DSVC_LAUNCH_CHECK();
-  return DSVC_OK;
-}
-
-// one denoiser evaluation: enqueue all kernels on `s`.  `slot` < 0: build the table for `ha` on the fly
-// (not allowed while capturing a graph); otherwise use the pre-built table of that slot.
-static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s, int slot = -1) {
+// one denoiser evaluation: enqueue all kernels on `s`
+static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
   const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
   const int B = h->B, T = h->Tmax;
-  if (step_eligible(h)) {
-    if (slot < 0) { slot = ha.tsel ? 1 : 0; DSVC_TRY(build_step_table(h, ha, slot, s)); }
-    return launch_step(h, slot, s);
-  }
-  // opt-in experiment (DSVC_DATAFLOW=1, slower -- see tc_gemm.cuh TcDep): tile-level dependencies between the 2L+3
-  // tensor-core kernels; the first kernel of an evaluation keeps the full griddepcontrol.wait (it follows a plain
-  // kernel and closes the previous step)
-  static int dataflow = -1;
-  if (dataflow < 0) { const char* ev = getenv("DSVC_DATAFLOW"); dataflow = (ev && ev[0] == '1') ? 1 : 0; }
-  const bool df = h->tc && dataflow && !tc_use_halo();
-  const int n_in = tc_ctas_per_mtile(B, T, C), n_dil = tc_ctas_per_mtile(B, T, 2 * C), n_out = n_dil;
-  const int n_skip = tc_ctas_per_mtile(B, T, C), n_head = tc_ctas_per_mtile(B, T, M);
-  const int per_eval = n_in + L * (n_dil + n_out) + n_skip + n_head;
-  int done = ha.dep_evals_before * per_eval;    // CTAs per frame tile completed before the next kernel (at step 0)
-  auto dep = [&](bool first) {
-    TcDep d{nullptr, nullptr, 0, 0, 0};
-    if (df) { d.cnt = h->dep_cnt.as<int>(); d.st = h->state.as<StepState>(); d.mode = first ? 0 : 1; d.base = done; d.per_step = per_eval; }
-    return d;
-  };
   {  // K0 input_projection + ReLU
     const EpiInProj::Params e = mk_inproj(h, ha.tsel);
-    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s, dep(true)));
+    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s));
     else DSVC_TRY(launch_fp32<EpiInProj>(h, base_params(h->XIN.f32.as<float>(), h->w_in.as<float>(), B, T, M, C, 1, 0), e, s));
-    done += n_in;
   }
   for (int l = 0; l < L; ++l) {
-    if (!df && fused_layers(h)) {
+    if (fused_layers(h)) {
       DSVC_TRY(enqueue_layer_fused(h, l, ha.tsel, s));
       continue;
     }
-    DSVC_TRY(enqueue_layer_conv(h, l, s, dep(false)));
-    done += n_dil;
-    DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s, dep(false)));
-    done += n_out;
+    DSVC_TRY(enqueue_layer_conv(h, l, s));
+    DSVC_TRY(enqueue_layer_out(h, l, ha.tsel, s));
   }
   {  // K4a skip_projection + ReLU
     const EpiSkipProj::Params e = mk_skip(h);
-    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s, dep(false)));
+    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s));
     else DSVC_TRY(launch_fp32<EpiSkipProj>(h, base_params(h->SP.f32.as<float>(), h->w_skip.as<float>(), B, T, C, C, 1, 0), e, s));
-    done += n_skip;
   }
   {  // K4b output_projection + sampler update
     const EpiHead::Params e = mk_head(h, ha);
-    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s, dep(false)));
+    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s));
     else DSVC_TRY(launch_fp32<EpiHead>(h, base_params(h->R.f32.as<float>(), h->w_head.as<float>(), B, T, C, M, 1, 0), e, s));
   }
-  return DSVC_OK;
-}
-
-static int reset_deps(dsvc_diffnet* h, cudaStream_t s) {
-  if (h->dep_cnt.p) DSVC_CUDA(cudaMemsetAsync(h->dep_cnt.p, 0, h->dep_cnt.bytes, s));
   return DSVC_OK;
 }
 
@@ -616,16 +499,12 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
   DSVC_TRY(h->cond_cl.reserve(n * H * 4));
   DSVC_TRY(h->lengths.reserve((size_t)B * 4));
   DSVC_TRY(h->state.reserve(sizeof(StepState)));
-  DSVC_TRY(h->dep_cnt.reserve((size_t)B * ceil_div(Tmax, TC_BM) * sizeof(int)));
   if (tc && (2 * C) % SK_BN == 0 && (long long)ceil_div(Tmax, TC_BM) * ((2 * C) / SK_BN) * B * SK_SPLIT <= 4 * h->num_sms)
     DSVC_TRY(h->sk_slab.reserve(tc_splitk_slab_bytes(B, Tmax, 2 * C)));
-  if (!h->gbar.p) {
-    DSVC_TRY(h->gbar.reserve(2 * sizeof(unsigned)));
-    DSVC_CUDA(cudaMemsetAsync(h->gbar.p, 0, 2 * sizeof(unsigned), s));
+  {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) h->num_sms = sms;
-    for (int i = 0; i < 2; ++i) DSVC_TRY(h->step_dev[i].reserve((size_t)(2 * L + 3) * sizeof(StepPhase)));
   }
   DSVC_TRY(h->Y.reserve(n * C, tc));
   if (h->pingpong) {
@@ -662,8 +541,7 @@ int dsvc_diffnet_eval(dsvc_diffnet_t* h, const float* spec, int32_t t, float* ou
   if (!h->prepared) { set_error("dsvc_diffnet_eval: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
   DSVC_REQUIRE(t >= 0 && t < h->cfg.num_timesteps, "diffusion step %d outside [0,%d)", t, h->cfg.num_timesteps);
   cudaStream_t s = (cudaStream_t)stream;
-  DSVC_TRY(reset_deps(h, s));
-  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t, 0);
+  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t, 0, 0ull, nullptr);
   DSVC_LAUNCH_CHECK();
   DSVC_TRY(load_x(h, spec, s));
   HeadArgs ha; ha.mode = HEAD_EVAL; ha.out = out;
@@ -695,8 +573,7 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
     return DSVC_ESTATE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  DSVC_TRY(reset_deps(h, s));
-  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0, 1);   // a valid step-table row
+  set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 0, 1, 0ull, nullptr);   // a valid step-table row
   DSVC_LAUNCH_CHECK();
   for (int i = 0; i < iters; ++i) {
     if (part == 0) DSVC_TRY(enqueue_layer_conv(h, layer, s));
@@ -736,22 +613,19 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
   cudaStream_t s = (cudaStream_t)stream;
   DSVC_TRY(load_x(h, x, s));
   if (t_start > 0) {
-    DSVC_TRY(reset_deps(h, s));
-    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t_start - 1, 1);
+    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), t_start - 1, 1, seed, noise);
     DSVC_LAUNCH_CHECK();
-    HeadArgs ha; ha.mode = HEAD_DDPM; ha.noise = noise; ha.seed = seed;
-    const bool persistent = step_eligible(h);
-    // persistent path: per-call arguments live in the phase table (refreshed here, stream-ordered), so the
-    // captured graph is independent of them; per-kernel path: they are baked into the kernel nodes
-    if (persistent) DSVC_TRY(build_step_table(h, ha, 0, s));
-    if (!h->g_ddpm_valid || (!persistent && (h->g_ddpm_noise != noise || h->g_ddpm_seed != seed))) {
+    // the per-call arguments (seed, external noise pointer) live in the device-side StepState, so the captured step
+    // graph is call-invariant: one capture per (B, Tmax)
+    HeadArgs ha; ha.mode = HEAD_DDPM;
+    if (!h->g_ddpm_valid) {
       DSVC_TRY(capture_graph(h, &h->g_ddpm, &h->g_ddpm_nodes, [&](cudaStream_t cs) -> int {
-        DSVC_TRY(enqueue_eval(h, ha, cs, 0));
+        DSVC_TRY(enqueue_eval(h, ha, cs));
         advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 0);
         DSVC_LAUNCH_CHECK();
         return DSVC_OK;
       }));
-      h->g_ddpm_valid = true; h->g_ddpm_noise = noise; h->g_ddpm_seed = seed;
+      h->g_ddpm_valid = true;
     }
     for (int i = 0; i < t_start; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm, s));
     g_launches.fetch_add(h->g_ddpm_nodes * (uint64_t)t_start, std::memory_order_relaxed);
@@ -769,23 +643,20 @@ int dsvc_sample_plms(dsvc_diffnet_t* h, float* x, int32_t t_start, int32_t inter
   // reversed(range(0, t_start, interval)): first t is the largest multiple of interval below t_start
   const int n_iter = t_start > 0 ? (t_start - 1) / interval + 1 : 0;
   if (n_iter > 0) {
-    DSVC_TRY(reset_deps(h, s));
-    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), (n_iter - 1) * interval, interval);
+    set_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), (n_iter - 1) * interval, interval, 0ull, nullptr);
     DSVC_LAUNCH_CHECK();
     // first iteration: two evaluations (diffusion.py:184-187)
     HeadArgs a; a.mode = HEAD_PLMS_FIRST; a.tsel = 0;
     DSVC_TRY(enqueue_eval(h, a, s));
-    HeadArgs b2; b2.mode = HEAD_PLMS_SECOND; b2.tsel = 1; b2.dep_evals_before = 1;
+    HeadArgs b2; b2.mode = HEAD_PLMS_SECOND; b2.tsel = 1;
     DSVC_TRY(enqueue_eval(h, b2, s));
     advance_state_kernel<<<1, 1, 0, s>>>(h->state.as<StepState>(), 1);
     DSVC_LAUNCH_CHECK();
     if (n_iter > 1) {
-      HeadArgs c; c.mode = HEAD_PLMS_NEXT; c.dep_evals_before = 1;   // iteration i (st->step == i) follows i+1 evaluations
-      const bool persistent = step_eligible(h);
-      if (persistent) DSVC_TRY(build_step_table(h, c, 0, s));   // slot 0 held the FIRST-eval table until here
+      HeadArgs c; c.mode = HEAD_PLMS_NEXT;
       if (!h->g_plms_valid) {
         DSVC_TRY(capture_graph(h, &h->g_plms, &h->g_plms_nodes, [&](cudaStream_t cs) -> int {
-          DSVC_TRY(enqueue_eval(h, c, cs, 0));
+          DSVC_TRY(enqueue_eval(h, c, cs));
           advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 1);
           DSVC_LAUNCH_CHECK();
           return DSVC_OK;

@@ -22,6 +22,9 @@ struct StepState {
   int step;     // number of completed steps (index of the noise slab to consume)
   int n_hist;   // PLMS: valid entries in the eps history (0..3)
   int head;     // PLMS: slot the current eps is written to (ring of 4)
+  // per-call DDPM arguments (device-resident so that the captured step graph does not depend on them)
+  unsigned long long seed;   // Philox key of the library's own N(0,1) stream
+  const float* noise;        // caller-provided noise [steps][B][1][M][Tmax], or null
 };
 
 // An operand "plane": the activation tensor a later contraction reads.  fp32 for the FFMA path;
@@ -293,8 +296,6 @@ struct EpiHead {
     Plane XIN;           // operand plane of input_projection for the next eval
     // DDPM
     const float* c_recip; const float* c_recipm1; const float* c_coef1; const float* c_coef2; const float* c_logvar;
-    const float* noise;  // [steps][B][1][M][Tmax] or null
-    unsigned long long seed;
     // PLMS
     const float* alphas_cumprod;
     float* hist;         // [4][B][Tmax][M] eps ring
@@ -349,12 +350,13 @@ struct EpiHead {
       const float cr = c.d.x, crm1 = c.d.y, c1 = c.d.z, c2 = c.d.w;
       const float sd = (t == 0) ? 0.0f : expf(mul_rn(0.5f, e.c_logvar[t]));
       float nz[4];
-      if (e.noise) {
+      const float* noise = e.st->noise;
+      if (noise) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nz[i] = __ldg(e.noise + (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p);
+        for (int i = 0; i < 4; ++i) nz[i] = __ldg(noise + (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p);
       } else {
         // library stream: one Philox4x32-10 call yields the 4 draws of this (step, item, frame, channel-quad)
-        const float4 q = philox_normal4(e.seed, 0x6e6f6973u, (((size_t)e.st->step * e.B + b) * (e.M >> 2) + (n >> 2)) * e.Tmax + p);
+        const float4 q = philox_normal4(e.st->seed, 0x6e6f6973u, (((size_t)e.st->step * e.B + b) * (e.M >> 2) + (n >> 2)) * e.Tmax + p);
         nz[0] = q.x; nz[1] = q.y; nz[2] = q.z; nz[3] = q.w;
       }
 #pragma unroll

@@ -178,11 +178,7 @@ int dsvc_mel_analysis(const dsvc_mel_config* cfg, const float* wav, int64_t n_sa
   int log2n = 0;
   while ((1 << log2n) < n) ++log2n;
   const size_t smem = (size_t)n * sizeof(double2) + (size_t)(n / 2) * sizeof(double2) + (size_t)(n / 2 + 1) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    DSVC_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  DSVC_TRY((ensure_dyn_smem<stft_mel_kernel>((int)smem)));
   stft_mel_kernel<<<(unsigned)T, 256, smem, (cudaStream_t)stream>>>(wav, (long long)n_samples, n, log2n, cfg->hop_size,
                                                                    (cfg->n_fft - cfg->hop_size) / 2, window, mel_basis, band_lo,
                                                                    band_hi, cfg->n_mels, cfg->clip_val, cfg->out_scale, mel_out);

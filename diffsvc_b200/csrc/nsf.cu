@@ -216,97 +216,6 @@ noise_conv_add_kernel(const float* __restrict__ har, const float* __restrict__ w
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Direct convolution for the narrow stages (C = 16 / 32 channels in and out): out = conv(lrelu(in)) + bias (+ res)
-// (+ out) (/ div), the EpiAffine semantics.  The implicit GEMM is a poor fit here (N = 16 / 32: a 256 x N tile spends
-// its time staging operands).  Here a block owns 256 output frames: the leaky_relu'ed input rows (with the dilated
-// halo) are staged once in shared memory (row pitch C+4 floats: conflict-free LDS.128 for 32 consecutive rows), the
-// whole weight tensor sits next to them as [k][ci][co], and a thread owns TWO frames (t, t+128) x all C channels:
-// per (tap, ci) one broadcast LDS.128 of weights feeds 8 FMAs -- FMA-issue bound, not LDS bound.
-// ---------------------------------------------------------------------------------------------
-constexpr int SMALL_PB = 256;                  // frames per block
-template <int C>
-__global__ void __launch_bounds__(128)
-conv_small_kernel(const float* __restrict__ in, const float* __restrict__ w /* [K][C out][C in] */, const float* __restrict__ bias,
-                  const float* __restrict__ res, float* __restrict__ out, int L, int K, int dil, float in_slope, int accumulate,
-                  float div) {
-  constexpr int LD = C + 4;
-  extern __shared__ __align__(16) float sm_small[];
-  float* wsm = sm_small;                       // [K][ci][co]
-  float* xs = sm_small + K * C * C;            // [SMALL_PB + 2*halo][LD]
-  const int halo = (K >> 1) * dil;
-  const int b = blockIdx.y, p0 = blockIdx.x * SMALL_PB;
-  for (int i = threadIdx.x; i < K * C * C; i += blockDim.x) {
-    const int k = i / (C * C), r = i % (C * C), ci = r / C, co = r % C;
-    wsm[i] = __ldg(w + ((size_t)k * C + co) * C + ci);
-  }
-  const float* inb = in + (size_t)b * L * C;
-  const int rows = SMALL_PB + 2 * halo;
-  for (int i = threadIdx.x; i < rows * (C / 4); i += blockDim.x) {
-    const int r = i / (C / 4), c4 = i % (C / 4);
-    const int q = p0 - halo + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q >= 0 && q < L) {
-      v = __ldg(reinterpret_cast<const float4*>(inb + (size_t)q * C + c4 * 4));
-      if (in_slope != 1.0f) { v.x = lrelu_(v.x, in_slope); v.y = lrelu_(v.y, in_slope); v.z = lrelu_(v.z, in_slope); v.w = lrelu_(v.w, in_slope); }
-    }
-    *reinterpret_cast<float4*>(xs + (size_t)r * LD + c4 * 4) = v;
-  }
-  __syncthreads();
-  float acc[2][C];
-#pragma unroll
-  for (int u = 0; u < 2; ++u)
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[u][c] = 0.f;
-  const int t = threadIdx.x;
-  for (int k = 0; k < K; ++k) {
-    const float* x0 = xs + (size_t)(t + k * dil) * LD;          // frame p0 + t, tap k  (row index = t + halo + (k - K/2)*dil)
-    const float* x1 = x0 + (size_t)128 * LD;                    // frame p0 + t + 128
-    const float* wk = wsm + (size_t)k * C * C;
-#pragma unroll
-    for (int c4 = 0; c4 < C; c4 += 4) {
-      const float4 a0 = *reinterpret_cast<const float4*>(x0 + c4);
-      const float4 a1 = *reinterpret_cast<const float4*>(x1 + c4);
-      const float xa[4] = {a0.x, a0.y, a0.z, a0.w}, xb[4] = {a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int co = 0; co < C; co += 4) {
-          const float4 ww = *reinterpret_cast<const float4*>(wk + (c4 + i) * C + co);
-          acc[0][co] = fmaf(xa[i], ww.x, acc[0][co]); acc[0][co + 1] = fmaf(xa[i], ww.y, acc[0][co + 1]);
-          acc[0][co + 2] = fmaf(xa[i], ww.z, acc[0][co + 2]); acc[0][co + 3] = fmaf(xa[i], ww.w, acc[0][co + 3]);
-          acc[1][co] = fmaf(xb[i], ww.x, acc[1][co]); acc[1][co + 1] = fmaf(xb[i], ww.y, acc[1][co + 1]);
-          acc[1][co + 2] = fmaf(xb[i], ww.z, acc[1][co + 2]); acc[1][co + 3] = fmaf(xb[i], ww.w, acc[1][co + 3]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int p = p0 + t + u * 128;
-    if (p >= L) continue;
-    const size_t o = ((size_t)b * L + p) * C;
-#pragma unroll
-    for (int c = 0; c < C; c += 4) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-      float v[4] = {acc[u][c] + bv.x, acc[u][c + 1] + bv.y, acc[u][c + 2] + bv.z, acc[u][c + 3] + bv.w};
-      if (res) {
-        const float4 r = *reinterpret_cast<const float4*>(res + o + c);
-        v[0] = add_rn(v[0], r.x); v[1] = add_rn(v[1], r.y); v[2] = add_rn(v[2], r.z); v[3] = add_rn(v[3], r.w);
-      }
-      if (accumulate) {
-        const float4 r = *reinterpret_cast<const float4*>(out + o + c);
-        v[0] = add_rn(r.x, v[0]); v[1] = add_rn(r.y, v[1]); v[2] = add_rn(r.z, v[2]); v[3] = add_rn(r.w, v[3]);
-      }
-      if (div != 1.0f) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = div_rn(v[i], div);
-      }
-      *reinterpret_cast<float4*>(out + o + c) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-  }
-}
-
 // conv_post (Cout = 1, k = 7) on leaky_relu(x, 0.01) then tanh (models.py:383-385)
 __global__ void conv_post_tanh_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                       float* __restrict__ wav, int L, int C, int K, float slope) {
@@ -444,29 +353,6 @@ static int launch_affine(const ConvGemmParams& p, const EpiAffine::Params& e, cu
 // out[b][p][:] (+)= conv(lrelu(in)) + bias (+ res), dilation d, "same" padding
 static int conv_same(const ConvW& c, const float* in, float* out, const float* res, int B, int L, int dil, float slope,
                      int accumulate, float div, cudaStream_t s) {
-  static int small = -1;
-  // opt-in experiment: measured equal-to-slower than the implicit GEMM (7.05 vs 6.86 ms per 10 s clip) -- a
-  // broadcast LDS.128 still costs four shared-memory wavefronts, so the weight reads bound it, not the FMAs
-  if (small < 0) { const char* ev = getenv("DSVC_NSF_SMALLCONV"); small = (ev && ev[0] == '1') ? 1 : 0; }
-  if (small && c.Cin == c.Cout && (c.Cout == 16 || c.Cout == 32) && c.K % 2 == 1) {
-    const int halo = (c.K / 2) * dil;
-    const size_t smem = ((size_t)c.K * c.Cout * c.Cin + (size_t)(SMALL_PB + 2 * halo) * (c.Cout + 4)) * 4;
-    if (smem <= 160 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        DSVC_CUDA(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        DSVC_CUDA(cudaFuncSetAttribute(conv_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-      }
-      dim3 grid(ceil_div(L, SMALL_PB), B);
-      if (c.Cout == 16)
-        conv_small_kernel<16><<<grid, 128, smem, s>>>(in, c.w.as<float>(), c.b.as<float>(), res, out, L, c.K, dil, slope, accumulate, div);
-      else
-        conv_small_kernel<32><<<grid, 128, smem, s>>>(in, c.w.as<float>(), c.b.as<float>(), res, out, L, c.K, dil, slope, accumulate, div);
-      DSVC_LAUNCH_CHECK();
-      return DSVC_OK;
-    }
-  }
   ConvGemmParams p{};
   p.A = in; p.W = c.w.as<float>(); p.B = B; p.Lin = L; p.Cin = c.Cin; p.Cout = c.Cout; p.taps = c.K; p.rows = L;
   p.in_stride = 1; p.in_off = -((c.K * dil - dil) / 2); p.tap_step = dil; p.nphase = 1; p.tpad = 0; p.in_slope = slope;
@@ -502,10 +388,6 @@ static int nsf_build_maps(dsvc_nsf* h, int B, int T) {
     auto planes = [&](TcGemmMaps& g, const PlaneBuf& pb) -> int {
       DSVC_TRY(tc_make_a_map(&g.a_hi, pb.hi.as<__half>(), B, len, ch));
       DSVC_TRY(tc_make_a_map(&g.a_lo, pb.lo.as<__half>(), B, len, ch));
-      DSVC_TRY(tc_make_a_map(&g.a64_hi, pb.hi.as<__half>(), B, len, ch, 64));
-      DSVC_TRY(tc_make_a_map(&g.a64_lo, pb.lo.as<__half>(), B, len, ch, 64));
-      DSVC_TRY(tc_make_a_map(&g.a32_hi, pb.hi.as<__half>(), B, len, ch, 32));
-      DSVC_TRY(tc_make_a_map(&g.a32_lo, pb.lo.as<__half>(), B, len, ch, 32));
       return DSVC_OK;
     };
     DSVC_TRY(planes(m.px, h->PX));

@@ -37,9 +37,6 @@ struct TcGemmMaps {
   CUtensorMap b_hi, b_lo;        // weights, box {64, 128 rows}   (BN = 128 tiles)
   CUtensorMap b32_hi, b32_lo;    // weights, box {64, 32 rows}    (BN = 64 tiles: two boxes per stage)
   CUtensorMap b64_hi, b64_lo;    // weights, box {64, 64 rows}    (BN = 256 gate|filter tiles: four boxes per stage)
-  CUtensorMap a144_hi, a144_lo;  // dilated-conv layers only: box {64 ch, 144 frames} (tc_conv3.cuh)
-  CUtensorMap a64_hi, a64_lo;    // activation slices for cluster multicast: box {64 ch, 64 frames} (CS = 2)
-  CUtensorMap a32_hi, a32_lo;    //                                           box {64 ch, 32 frames} (CS = 4)
 };
 struct TcMaps {
   TcGemmMaps in, skip, head;
@@ -122,7 +119,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#ifdef DSVC_WATCHDOG   // debug builds: a lost arrive fails loudly instead of hanging the GPU
   const long long t0 = clock64();
+#endif
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -130,10 +129,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000ll) {   // ~2 s: a lost arrive must fail loudly, not hang the GPU
+#ifdef DSVC_WATCHDOG
+    if (clock64() - t0 > 4000000000ll) {   // ~2 s
       printf("libdsvc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
+#endif
   }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
@@ -145,17 +146,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// multicast variants: the tile (and its complete_tx) lands at the same smem offset in every CTA of the mask
-__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -180,50 +170,6 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// Tile-level dependencies between the kernels of one evaluation ("dataflow" mode).  Every CTA bumps a
-// per-(item, frame-tile) counter when its outputs are globally visible; a CTA of the NEXT kernel starts as soon as
-// ALL CTAs of the previous kernel for frame tiles m-1, m, m+1 are done (m+-1: the dilated conv's halo, and
-// the write-after-read on the plane it overwrites) instead of waiting for the whole previous grid to drain
-// (griddepcontrol.wait).  With griddepcontrol.launch_dependents at kernel entry the next kernel's CTAs are
-// already resident on the idle SMs; counters are monotonic over a sampler call:
-//   expected(kernel k, step s) = base_k + s * per_step,  base_k = CTAs per frame tile of all earlier kernels.
-// Measured (one clip, B200): correct (parity unchanged) but SLOWER than griddepcontrol.wait, 564 vs 398 us per
-// step -- the device-scope fence + atomic + polled acquire chain costs more than the hardware's grid-completion
-// path, and with one wave of equal tiles there is no tail to hide.  Opt-in: DSVC_DATAFLOW=1.
-struct TcDep {
-  int* cnt;              // [B * m_tiles]; null: no counting
-  const StepState* st;   // st->step = completed steps of this sampler call
-  int mode;              // 0: griddepcontrol.wait, 1: counters
-  int base, per_step;
-};
-
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// one lane polls, the warp follows
-__device__ __forceinline__ void dep_wait(const TcDep& d, int b, int mt, int m_tiles, int lane) {
-  if (d.mode == 0) { pdl_wait(); return; }
-  if (lane == 0) {
-    const int expected = d.base + d.st->step * d.per_step;
-    const int lo = mt > 0 ? mt - 1 : 0, hi = mt + 1 < m_tiles ? mt + 1 : m_tiles - 1;
-    const long long t0 = clock64();
-    for (int m = lo; m <= hi; ++m) {
-      const unsigned* p = reinterpret_cast<const unsigned*>(d.cnt + b * m_tiles + m);
-      while ((int)ld_acquire_gpu_u32(p) < expected) {
-        if (clock64() - t0 > 4000000000ll) {
-          printf("libdsvc: tile dependency wait timed out (block %d,%d,%d expected %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, expected);
-          __trap();
-        }
-      }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");   // the producer's outputs are read by TMA (async proxy) below
-  }
-  __syncwarp();
-}
 
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -420,15 +366,11 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-// CS = thread-block-cluster size along the channel-tile axis.  The CS CTAs of a cluster compute the same
-// 128 frames for different channel tiles, so each loads 1/CS of the activation tile and multicasts it
-// to its peers: L2 -> SM activation traffic per CTA drops by CS (the mainloop is bound by operand
-// delivery, ~64 B/clk/SM and ~6.3 KB/clk chip-wide).
-template <class Epi, int BN, int CS>
+template <class Epi, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes, const TcDep dep) {
+               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -464,7 +406,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CS);            // every CTA of the cluster must have drained the stage
+      mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -475,13 +417,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   if (warp == 3) TL_MARK(0);   // setup done
-  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
-  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
   // weight tile(s) of pipeline iteration `it` into stage s (weights are constants: no dependency on
   // the previous kernel, so the first STAGES of them are requested before griddepcontrol.wait)
@@ -527,16 +466,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   auto load_a = [&](int it, int s) {
     const int tap = it / kblocks, kb = it - tap * kblocks;
     const int frame = m0 + (tap - (taps >> 1)) * dil;   // centred odd kernel (taps = 1: the frame itself)
-    if constexpr (CS == 1) {
-      tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
-      if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
-    } else {
-      // this CTA's slice of the tile (TC_BM/CS frames), delivered to all CS CTAs
-      constexpr int SL = TC_BM / CS;
-      const uint32_t off = crank * (uint32_t)(SL * TC_BK * 2);
-      tma_load_3d_mc(&tmAh, full_bar(s), tile_a(s, 0) + off, kb * TC_BK, frame + (int)crank * SL, b, cmask);
-      if (three) tma_load_3d_mc(&tmAl, full_bar(s), tile_a(s, 1) + off, kb * TC_BK, frame + (int)crank * SL, b, cmask);
-    }
+    tma_load_3d(&tmAh, full_bar(s), tile_a(s, 0), kb * TC_BK, frame, b);
+    if (three) tma_load_3d(&tmAl, full_bar(s), tile_a(s, 1), kb * TC_BK, frame, b);
   };
 
   if (warp == 0) {
@@ -550,7 +481,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
     }
     __syncwarp();
-    dep_wait(dep, b, (int)blockIdx.x, (int)gridDim.x, lane);   // activations below were written by the previous kernel
+    pdl_wait();                                 // activations below were written by the previous kernel
     if (elect_one_sync()) {
       for (int it = 0; it < pre; ++it) load_a(it, it);
     }
@@ -598,29 +529,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
           }
         }
-        // frees the smem stage once these MMAs have read it (in every CTA of the cluster: peers multicast into it)
-        if constexpr (CS == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
+        umma_commit(empty_bar(s));                         // frees the smem stage once these MMAs have read it
         if (it == total - 1) umma_commit(tmem_full_bar);   // accumulator complete
       }
       __syncwarp();
     }
     TL_MARK(2);                             // all MMAs issued
   }
-  dep_wait(dep, b, (int)blockIdx.x, (int)gridDim.x, lane);   // every warp: the epilogue reads tensors the previous kernel wrote
+  pdl_wait();   // every warp: the epilogue reads tensors the previous kernel wrote
 #ifdef DSVC_TIMELINE
   tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three, tl0);
 #else
   tc_epilogue<Epi, BN>(ep, smem_raw, smem_base, tmem_base, tmem_full_bar, 0u, T, N, m0, (int)blockIdx.y, b, warp, lane, three);
 #endif
   if (warp == 4) TL_MARK(6);               // epilogue done
-  if (dep.cnt != nullptr) {                // this tile's outputs are visible device-wide ...
-    __threadfence();
-    asm volatile("fence.proxy.async;" ::: "memory");
-  }
   tc_fence_before();
   __syncthreads();
-  if (dep.cnt != nullptr && threadIdx.x == 0) atomicAdd(dep.cnt + b * (int)gridDim.x + (int)blockIdx.x, 1);   // ... before it counts as done
-  if constexpr (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
@@ -676,77 +600,38 @@ static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, in
   return DSVC_OK;
 }
 
-inline bool tc_use_pdl() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DSVC_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-
-inline int tc_cluster_pref() {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("DSVC_TC_CLUSTER"); v = e ? atoi(e) : -1; }
-  return v;   // -1 = automatic, 1 = off, 2 / 4 = forced upper bound
-}
-
-template <class Epi, int BN, int CS>
-int tc_launch_cs(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-                 cudaStream_t s, const TcDep& dep) {
-  static bool attr_set = false;
-  auto kern = tc_gemm_kernel<Epi, BN, CS>;
-  if (!attr_set) {
-    DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
-    attr_set = true;
-  }
+template <class Epi, int BN>
+int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
+                 cudaStream_t s) {
+  DSVC_TRY((ensure_dyn_smem<tc_gemm_kernel<Epi, BN>>(TcCfg<BN>::SMEM)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ceil_div(T, TC_BM), ceil_div(N, BN), B);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (tc_use_pdl()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (CS > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
-    attr[na].val.clusterDim.y = CS;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = na;
+  cfg.numAttrs = 1;
   const bool b64 = (BN == 256) && Epi::kPair;
   const CUtensorMap& bh = (BN == 64) ? m.b32_hi : (b64 ? m.b64_hi : m.b_hi);
   const CUtensorMap& bl = (BN == 64) ? m.b32_lo : (b64 ? m.b64_lo : m.b_lo);
-  const CUtensorMap& ah = (CS == 1) ? m.a_hi : (CS == 2 ? m.a64_hi : m.a32_hi);
-  const CUtensorMap& al = (CS == 1) ? m.a_lo : (CS == 2 ? m.a64_lo : m.a32_lo);
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, e, T, K, N, taps, dil, passes, dep));
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi, BN>, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, passes));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }
 
-template <class Epi, int BN>
-int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-                 cudaStream_t s, const TcDep& dep) {
-  const int ntiles = ceil_div(N, BN);
-  // Cluster multicast of the activation tile is correct but measured neutral-to-slower: the mainloop is bound
-  // by shared-memory bandwidth (TMA fill + UMMA operand reads ~ 128 B/clk/SM), which multicast does not
-  // reduce.  Opt-in via DSVC_TC_CLUSTER=2|4.
-  const int pref = tc_cluster_pref();
-  const int cap = (pref < 0 || BN == 256) ? 1 : pref;
-  if (cap >= 4 && ntiles % 4 == 0) return tc_launch_cs<Epi, BN, 4>(m, e, B, T, K, N, taps, dil, passes, s, dep);
-  if (cap >= 2 && ntiles % 2 == 0) return tc_launch_cs<Epi, BN, 2>(m, e, B, T, K, N, taps, dil, passes, s, dep);
-  return tc_launch_cs<Epi, BN, 1>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+// DSVC_TC_BN=64|128|256 forces the tile width (read per call: the parity tests switch it per handle)
+inline int tc_forced_bn() {
+  const char* e = getenv("DSVC_TC_BN");
+  return e ? atoi(e) : -1;
 }
 
 // 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
 // 1.7+ waves the narrower tiles re-fetch the activation tile twice as often and lose ~35 %)
 inline bool tc_narrow_tiles(int B, int T, int N) {
-  static int forced = -2;
-  if (forced == -2) { const char* e = getenv("DSVC_TC_BN"); forced = e ? atoi(e) : -1; }
+  const int forced = tc_forced_bn();
   if (forced == 64) return true;
   if (forced == 128) return false;
   return (long long)ceil_div(T, TC_BM) * ceil_div(N, 128) * B < 148;
@@ -754,8 +639,7 @@ inline bool tc_narrow_tiles(int B, int T, int N) {
 
 // 256-wide tiles (best operand reuse: ~235 vs 281 smem bytes per column per K-step) once they fill the GPU
 inline bool tc_wide_tiles(int B, int T, int N) {
-  static int forced = -2;
-  if (forced == -2) { const char* e = getenv("DSVC_TC_BN"); forced = e ? atoi(e) : -1; }
+  const int forced = tc_forced_bn();
   if (N % 256 != 0) return false;
   if (forced == 256) return true;
   if (forced == 64 || forced == 128) return false;
@@ -773,12 +657,12 @@ inline int tc_ctas_per_mtile(int B, int T, int N) { return ceil_div(N, tc_pick_b
 
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-              cudaStream_t s, const TcDep& dep = TcDep{nullptr, nullptr, 0, 0, 0}) {
+              cudaStream_t s) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
   const int bn = tc_pick_bn(B, T, N);
-  if (bn == 64) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s, dep);
-  if (bn == 256) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s, dep);
-  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s, dep);
+  if (bn == 64) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s);
+  if (bn == 256) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s);
+  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s);
 }
 
 }  // namespace dsvc

@@ -310,10 +310,14 @@ inline bool tc_layer_shape_ok(int B, int T, int C) {
 // Sets the function attributes on first use; cached per cluster size.  Called from dsvc_diffnet_prepare (outside any
 // stream capture).  *usable = 0: the caller keeps the two separate kernels.
 inline int tc_layer_probe(int nt, int* usable) {   // *usable = max co-resident clusters (0: not schedulable)
-  static int cache[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  static int cache[64][17];                        // per device: 0 = not probed yet, -1 = not schedulable, else clusters
   *usable = 0;
   if (nt < 1 || nt > 16) return DSVC_OK;
-  if (cache[nt] < 0) {
+  int dev = 0;
+  DSVC_CUDA(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  int v = tracked ? cache[dev][nt] : 0;
+  if (v == 0) {
     auto kern = tc_layer_kernel;
     DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<LY_BN>::SMEM));
     if (nt > 8) DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -331,9 +335,10 @@ inline int tc_layer_probe(int nt, int* usable) {   // *usable = max co-resident 
     int clusters = 0;
     const cudaError_t e = cudaOccupancyMaxActiveClusters(&clusters, kern, &q);
     if (e != cudaSuccess) cudaGetLastError();
-    cache[nt] = (e == cudaSuccess && clusters >= 1) ? clusters : 0;
+    v = (e == cudaSuccess && clusters >= 1) ? clusters : -1;
+    if (tracked) cache[dev][nt] = v;
   }
-  *usable = cache[nt];
+  *usable = v > 0 ? v : 0;
   return DSVC_OK;
 }
 
@@ -365,11 +370,9 @@ inline int tc_layer_launch(const TcGemmMaps& md, const TcGemmMaps& mo, const TcG
   attr[na].val.clusterDim.y = nt;
   attr[na].val.clusterDim.z = 1;
   ++na;
-  if (tc_use_pdl()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
   const bool pf = mnext != nullptr && tc_layer_prefetch_next();

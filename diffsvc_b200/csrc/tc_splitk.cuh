@@ -231,12 +231,8 @@ template <class Epi>
 int tc_splitk_launch(const TcGemmMaps& m, const typename Epi::Params& e, float* slab, int B, int T, int K, int N, int dil,
                      cudaStream_t s) {
   DSVC_REQUIRE(K % TC_BK == 0 && N % SK_BN == 0, "tc_splitk_launch: K=%d N=%d", K, N);
-  static bool attr_set = false;
   auto kern = tc_splitk_kernel<Epi>;
-  if (!attr_set) {
-    DSVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<SK_BN>::SMEM));
-    attr_set = true;
-  }
+  DSVC_TRY((ensure_dyn_smem<tc_splitk_kernel<Epi>>(TcCfg<SK_BN>::SMEM)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ceil_div(T, TC_BM), (N / SK_BN) * SK_SPLIT, B);
   cfg.blockDim = dim3(TC_THREADS);
@@ -244,11 +240,9 @@ int tc_splitk_launch(const TcGemmMaps& m, const typename Epi::Params& e, float* 
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (tc_use_pdl()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   attr[na].id = cudaLaunchAttributeClusterDimension;
   attr[na].val.clusterDim.x = 1;
   attr[na].val.clusterDim.y = SK_SPLIT;
