@@ -2,16 +2,21 @@
 """bench.py -- BASELINE.json's headline metric on synthetic inputs.
 
   metric  : audio-sec/s (= 1/RTF) for 1000-step DDPM @ 44.1 kHz, NSF-HiFiGAN vocoder
-  workload: BASELINE.json configs[1]: one 10 s clip (862 mel frames, 128 bins), per GPU
-            (`--batch B` / `--frames T` widen it; at N > 1 every rank runs its own clip(s) -- weak
-            scaling -- and the final waveforms are all-gathered with NCCL inside the timed step)
-  a "step": one full pass of the hot path over the batch: 1000 DDPM denoising steps through the
-            20-layer WaveNet, denormalise + clip, NSF-HiFiGAN mel -> waveform.
+  workload: BASELINE.json configs[1]: one 10 s clip (862 mel frames, 128 bins) per GPU.  At N > 1 every rank runs
+            its own clip (weak scaling) and the final waveforms are all-gathered with NCCL inside the timed step.
+  a "step": one full pass of the hot path over the batch: 1000 DDPM denoising steps through the 20-layer WaveNet,
+            denormalise + clip, NSF-HiFiGAN mel -> waveform.
 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path: the oracle port,
-                                                            rank 0 only, bounded sample per step)
-Prints ONE JSON line on rank 0.
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU modules from baseline/_ref,
+                                                            rank 0 only, a bounded sample per step)
+Prints ONE JSON line on rank 0.  Besides the contract keys the line carries (verdict r1, items 2 and 6):
+  roofline        dominant kernel timed live; frac (algorithmic), frac_executed (x3 passes), the parity-mode ceiling
+  layer_budget    conv / out-projection kernel us, us per DDPM step, what is left per kernel boundary
+  cfg3_sliced_batch   BASELINE configs[3]: 8 ragged slices per GPU (64 at N = 8) through sharding.partition_slices
+                  -> per-rank ragged batch -> sharding.gather_waveforms (NCCL); per-rank busy times, gather us
+  extras (N = 1)  configs[2] (PNDM-25 latency), configs[4] (0.5 s chunk p50), stock-PyTorch-eager-on-B200 baseline
+  cpu_baseline    the reference's CPU path on this box's host cores (N = 1 only)
 """
 import argparse
 import json
@@ -27,11 +32,16 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+import synthetic as S  # noqa: E402  (neutral fixtures: seeded weights / utterances; not the checker)
+
 SR, HOP, MEL, HID = 44100, 512, 128, 256
 FLOP_EVAL_PER_FRAME = 47_677_440         # DiffNet eval, conditioner projections hoisted
 FLOP_COND_PER_FRAME = 7_864_320          # one-off conditioner projections of all 20 layers
 FLOP_CONV_PER_FRAME = 2 * 3 * 384 * 768  # dilated conv of one layer (the dominant kernel)
+FLOP_OUT_PER_FRAME = 2 * 384 * 768       # output projection of one layer
 FLOP_VOC_PER_FRAME = 648_527_872
+PASSES = 3                               # fp16 hi/lo split: xh*wh + xh*wl + xl*wh on the tensor pipe
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def parse():
@@ -44,7 +54,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=862, help="mel frames per clip (862 = 10 s @ 44.1 kHz)")
     ap.add_argument("--ddpm-steps", type=int, default=1000)
     ap.add_argument("--math", default="tc3f16", choices=["tc3f16", "fp32", "tc1f16"])
-    ap.add_argument("--ref-ddpm-sample", type=int, default=6, help="reference arm: DDPM steps timed per bench step")
+    ap.add_argument("--ref-ddpm-sample", type=int, default=20, help="reference arm: DDPM steps timed per bench step")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (skip cfg2/cfg3/cfg4/eager/cpu legs)")
     return ap.parse_args()
 
 
@@ -84,12 +95,11 @@ class ClockSampler:
 
 def synth_inputs(B, T, seed):
     """Synthetic utterances: hubert-like units at 50 fps gathered to T mel frames, log2-f0, all frames valid."""
-    from oracle import diffsvc_oracle as O
     g = torch.Generator().manual_seed(seed)
     Th = max(2, int(T * 50 * HOP / SR))
     hubert = torch.randn(B, Th, HID, generator=g) * 0.5
     mel2ph = (torch.arange(T, dtype=torch.float32) * (Th / T)).long().clamp(max=Th - 1)[None].repeat(B, 1) + 1
-    f0_hz = O.synth_f0(B, T, seed=seed + 1)
+    f0_hz = S.synth_f0(B, T, seed=seed + 1)
     f0 = torch.where(f0_hz > 0, torch.log2(f0_hz.clamp(min=1.0)), torch.zeros_like(f0_hz))   # norm_interp_f0 'log'
     return hubert, mel2ph, f0, f0_hz
 
@@ -97,85 +107,131 @@ def synth_inputs(B, T, seed):
 def build_models(math_mode, ddpm_steps):
     import diffsvc_b200 as D
     from diffsvc_b200.hparams import hparams, DEFAULTS_44K
-    from oracle import diffsvc_oracle as O
     hparams.clear(); hparams.update(DEFAULTS_44K); hparams["pndm_speedup"] = 1
-    sd = O.synth_diffnet_weights()
+    sd = S.synth_diffnet_weights()
     dn = D.DiffNet(MEL, math_mode=math_mode)
     dn.load_state_dict(sd, strict=True)
     gd = D.GaussianDiffusion(None, MEL, dn, timesteps=1000, K_step=ddpm_steps, loss_type="l2", spec_min=[-5.0], spec_max=[0.0])
     gd = gd.cuda().eval()
-    nsd = O.synth_nsf_weights(O.NSF_H_44K)
-    voc = D.NsfHifiGAN.from_state_dict(dict(O.NSF_H_44K), nsd, device="cuda")
+    nsd = S.synth_nsf_weights(S.NSF_H_44K)
+    voc = D.NsfHifiGAN.from_state_dict(dict(S.NSF_H_44K), nsd, device="cuda")
     return gd, voc, sd, nsd
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_threads_autotune(sd, T):
-    """Pick the torch thread count that runs one DiffNet eval fastest on this host (many-core boxes
-    oversubscribe badly on these small convs); the reference gets its best configuration."""
-    from oracle import diffsvc_oracle as O
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 1, MEL, T, generator=g); c = torch.randn(1, HID, T, generator=g)
-    best = None
-    ncpu = os.cpu_count() or 1
-    for n in sorted({min(ncpu, k) for k in (8, 16, 32, 64, ncpu)}):
-        torch.set_num_threads(n)
-        O.diffnet_forward(sd, x, torch.tensor([5]), c)
-        t0 = time.perf_counter()
-        O.diffnet_forward(sd, x, torch.tensor([5]), c)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[1]:
-            best = (n, dt)
-    torch.set_num_threads(best[0])
-    return best[0]
+class ReferenceCpu:
+    """The reference's CPU path for this workload: its OWN `GaussianDiffusion.forward(infer=True)` (network/diff/
+    diffusion.py:227-284) and `Generator.forward` (modules/nsf_hifigan/models.py:361-387) imported unmodified from
+    baseline/_ref (kind "reference"); the oracle port of the same modules when that copy is absent (kind "port")."""
 
+    def __init__(self, T, n_ddpm, device="cpu"):
+        self.T, self.n, self.device = T, n_ddpm, device
+        self.sd, self.nsd = S.synth_diffnet_weights(), S.synth_nsf_weights(S.NSF_H_44K)
+        self.kind = "reference" if os.path.isdir(os.path.join(REF_DIR, "network", "diff")) else "port"
+        if self.kind == "reference":
+            os.environ["DIFFSVC_REFERENCE_ROOT"] = REF_DIR
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import ref_harness as rh
+            hp = rh.install()
+            diffusion, net = rh.import_diffusion()
+            models = rh.import_nsf_models()
+            from modules.nsf_hifigan.env import AttrDict
+            self.gd = diffusion.GaussianDiffusion(None, MEL, net.DiffNet(MEL), timesteps=1000, K_step=n_ddpm, loss_type="l2",
+                                                  spec_min=[-5.0], spec_max=[0.0]).eval()
+            self.gd.denoise_fn.load_state_dict(self.sd, strict=True)
+            self.gen = models.Generator(AttrDict(S.NSF_H_44K)).eval()
+            self.gen.remove_weight_norm()
+            self.gen.load_state_dict(self.nsd)
+            self.gd.to(device); self.gen.to(device)
+            hp["pndm_speedup"] = 1
+        else:
+            from oracle import diffsvc_oracle as O
+            self.O = O
+            self.sched = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+        self.inputs = synth_inputs(1, T, seed=5)
 
-def cpu_sample(sd, nsd, T, n_ddpm, seed):
-    """A bounded sample of the workload on the host: n_ddpm DDPM steps + one vocoder pass of ONE clip.
-    Returns (seconds for the DDPM sample, seconds for the vocoder pass)."""
-    from oracle import diffsvc_oracle as O
-    g = torch.Generator().manual_seed(seed)
-    cond = torch.randn(1, HID, T, generator=g) * 0.5
-    x = torch.randn(1, 1, MEL, T, generator=g)
-    noise = torch.randn(n_ddpm, 1, 1, MEL, T, generator=g)
-    sched = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        x = O.sample(sd, sched, cond, x, n_ddpm, noise)
-        t1 = time.perf_counter()
-        mel = O.mel_from_x(x, torch.tensor([[[-5.0]]]), torch.tensor([[[0.0]]])).clamp(-6.0, 1.5)
-        f0 = O.synth_f0(1, T)
-        O.spec2wav(nsd, O.NSF_H_44K, mel, f0, torch.rand(1, 9, generator=g), torch.randn(1, T * HOP, 9, generator=g))
-        t2 = time.perf_counter()
-    return t1 - t0, t2 - t1
+    def eval_once(self):
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(1, 1, MEL, self.T, generator=g).to(self.device); c = torch.randn(1, HID, self.T, generator=g).to(self.device)
+        t = torch.tensor([5], device=self.device)
+        with torch.no_grad():
+            if self.kind == "reference":
+                self.gd.denoise_fn(x, t, c)
+            else:
+                self.O.diffnet_forward(self.sd, x, t, c)
+
+    def autotune_threads(self):
+        """The thread count that runs one DiffNet eval fastest on this host (many-core boxes oversubscribe badly on
+        these small convs); the reference gets its best configuration."""
+        best, ncpu = None, os.cpu_count() or 1
+        for n in sorted({min(ncpu, k) for k in (8, 16, 32, 64, ncpu)}):
+            torch.set_num_threads(n)
+            self.eval_once()
+            t0 = time.perf_counter(); self.eval_once(); dt = time.perf_counter() - t0
+            if best is None or dt < best[1]:
+                best = (n, dt)
+        torch.set_num_threads(best[0])
+        return best[0]
+
+    def sample(self):
+        """n DDPM steps (through the public forward) + one vocoder pass of ONE clip -> (s sampler, s vocoder)."""
+        hubert, mel2ph, f0, f0_hz = (t.to(self.device) for t in self.inputs)
+        sync = torch.cuda.synchronize if self.device != "cpu" else (lambda: None)
+        with torch.no_grad():
+            sync(); t0 = time.perf_counter()
+            if self.kind == "reference":
+                import contextlib
+                with contextlib.redirect_stderr(open(os.devnull, "w")):        # tqdm progress bars
+                    ret = self.gd(hubert, mel2ph, None, None, f0.clone(), None, None, infer=True)
+                mel = ret["mel_out"]
+            else:
+                O = self.O
+                g = torch.Generator().manual_seed(1)
+                cond = torch.randn(1, HID, self.T, generator=g) * 0.5
+                x = torch.randn(1, 1, MEL, self.T, generator=g)
+                noise = torch.randn(self.n, 1, 1, MEL, self.T, generator=g)
+                mel = O.mel_from_x(O.sample(self.sd, self.sched, cond, x, self.n, noise), torch.tensor([[[-5.0]]]), torch.tensor([[[0.0]]]))
+            sync(); t1 = time.perf_counter()
+            mel = mel.clamp(-6.0, 1.5)                                           # after_infer clip (infer_tool.py:183)
+            if self.kind == "reference":
+                self.gen((2.30259 * mel).transpose(1, 2), f0_hz)                  # nsf_hifigan.py:39-43
+            else:
+                g = torch.Generator().manual_seed(2)
+                self.O.spec2wav(self.nsd, S.NSF_H_44K, mel, f0_hz, torch.rand(1, 9, generator=g), torch.randn(1, self.T * HOP, 9, generator=g))
+            sync(); t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
 
 
 def run_reference(args, rank):
-    """`--impl reference`: the reference's CPU path (oracle port of its torch modules, all host threads it
-    can use), rank 0 only.  Each bench step times a bounded sample and extrapolates linearly to the
-    full 1000-step clip; the JSON says so in cpu_baseline.sample."""
+    """`--impl reference`: rank 0 only.  Each bench step times a bounded sample (n of 1000 DDPM steps + one vocoder
+    pass of one clip); `value` extrapolates the DDPM part linearly to the full clip, `ms_per_step` is what was
+    actually timed (so steps x ms_per_step is the wall time of the timed region)."""
     if rank != 0:
         return
-    from oracle import diffsvc_oracle as O
-    sd, nsd = O.synth_diffnet_weights(), O.synth_nsf_weights(O.NSF_H_44K)
     T, n = args.frames, args.ref_ddpm_sample
-    threads = cpu_threads_autotune(sd, T)
-    times = []
+    ref = ReferenceCpu(T, n)
+    threads = ref.autotune_threads()
+    per_clip, timed = [], []
     for i in range(args.warmup + args.steps):
-        td, tv = cpu_sample(sd, nsd, T, n, seed=100 + i)
+        td, tv = ref.sample()
         if i >= args.warmup:
-            times.append(td / n * args.ddpm_steps + tv)
+            per_clip.append(td / n * args.ddpm_steps + tv); timed.append(td + tv)
     audio = T * HOP / SR
-    per_clip = sum(times) / len(times)
-    val = audio / per_clip
-    line = base_line(args, val, per_clip * 1000.0 * args.batch)
-    line.update({"impl": "reference", "dtype": "f32", "gpu_launches": 0,
-                 "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": threads, "kind": "port",
-                                  "sample": "%d of %d DDPM steps + 1 NSF-HiFiGAN pass of one %d-frame clip per bench step, "
-                                            "DDPM part extrapolated linearly; torch CPU fp32, %d threads (autotuned of %d cpus)"
-                                            % (n, args.ddpm_steps, T, threads, os.cpu_count() or 1)},
+    clip_s = sum(per_clip) / len(per_clip)
+    val = audio / clip_s
+    line = base_line(args, val, sum(timed) / len(timed) * 1000.0)
+    line.update({"impl": "reference", "dtype": "f32", "gpu_launches": 0, "extrapolated_ms_per_clip": clip_s * 1000.0,
+                 "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": threads, "kind": ref.kind,
+                                  "sample": "%d of %d DDPM steps + 1 NSF-HiFiGAN pass of one %d-frame clip per bench step (ms_per_step = "
+                                            "that sample), DDPM part extrapolated linearly to the clip; %s, torch CPU fp32, %d threads "
+                                            "(autotuned of %d cpus)" % (n, args.ddpm_steps, T, _kind_text(ref.kind), threads, os.cpu_count() or 1)},
                  "e2e": {"value": val, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
+
+
+def _kind_text(kind):
+    return ("the reference's own GaussianDiffusion.forward + Generator.forward from baseline/_ref" if kind == "reference"
+            else "oracle port of the reference modules (baseline/_ref absent)")
 
 
 def base_line(args, value, ms_per_step):
@@ -190,6 +246,125 @@ def base_line(args, value, ms_per_step):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def event_ms(fn):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b), out
+
+
+def cfg3_sliced_batch(gd, voc, dist, rank, world, flush, n_warm=1, n_timed=2):
+    """BASELINE configs[3]: 8 ragged slices (~8 s +- 25 %) per GPU -- 64 on 8 GPUs --
+    partitioned longest-first onto the ranks, each rank runs its ragged sub-batch (per-item lengths) through the
+    1000-step sampler + vocoder, and ONE variable-length all-gather of the waveforms reassembles the job."""
+    from diffsvc_b200 import sharding
+    n_slices = 8 * world
+    g = torch.Generator().manual_seed(4242)
+    lengths = (689 * (0.75 + 0.5 * torch.rand(n_slices, generator=g))).round().long().tolist()
+    bins = sharding.partition_slices(lengths, world)
+    mine = bins[rank]
+    lens = [lengths[i] for i in mine]
+    T = max(lens)
+    hubert, mel2ph, f0, f0_hz = synth_inputs(len(mine), T, seed=900 + rank)
+    for k, n in enumerate(lens):                                     # ragged: frames beyond an item's length are padding
+        mel2ph[k, n:] = 0; f0[k, n:] = 0; f0_hz[k, n:] = 0
+    with torch.no_grad():
+        ret0 = gd.fs2(hubert.cuda(), mel2ph.cuda(), None, None, f0.cuda().clone(), None, None, skip_decoder=True, infer=True)
+    cond = ret0["decoder_inp"].transpose(1, 2).contiguous()
+    x0 = torch.randn(len(mine), 1, MEL, T, device="cuda")
+    f0hz_d = f0_hz.cuda()
+    busy, gather, total = [], [], []
+    for i in range(n_warm + n_timed):
+        if dist is not None:
+            dist.barrier()
+        flush.fill_(float(i)); torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        with torch.no_grad():
+            x = gd.sample(x0, cond, 1000, None, None, lengths=lens, seed=31 + i)
+            mel = gd.denorm_spec(x[:, 0].transpose(1, 2)).clamp(-6.0, 1.5)
+            # the vocoder has no per-item boundary: vocode each slice alone (B = 1 semantics, as infer_tool.py:277 does)
+            wavs = [voc.spec2wav_torch(mel[k:k + 1, :n], f0=f0hz_d[k:k + 1, :n], seed=8 * i + k) for k, n in enumerate(lens)]
+        e[1].record()
+        if dist is not None:
+            full = sharding.gather_waveforms(wavs, mine, n_slices, device=torch.device("cuda", torch.cuda.current_device()))
+            assert len(full) == n_slices and all(full[j].numel() == lengths[j] * HOP for j in range(n_slices))
+        e[2].record(); torch.cuda.synchronize()
+        if i >= n_warm:
+            busy.append(e[0].elapsed_time(e[1])); gather.append(e[1].elapsed_time(e[2])); total.append(e[0].elapsed_time(e[2]))
+    stats = torch.tensor([sum(busy) / n_timed, sum(gather) / n_timed, sum(total) / n_timed, float(sum(lens))], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        allst = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+    else:
+        allst = [stats]
+    allst = torch.stack(allst).cpu()
+    job_ms = float(allst[:, 2].max())
+    audio = sum(lengths) * HOP / SR
+    return {"workload": "BASELINE configs[3]: %d ragged slices (689 frames +- 25 %%, %.1f s audio in total), 1000-step DDPM + NSF-HiFiGAN, "
+                        "sharding.partition_slices -> ragged sub-batch per rank -> sharding.gather_waveforms" % (n_slices, audio),
+            "n_slices": n_slices, "audio_sec_per_s": audio / (job_ms / 1000.0), "job_ms": job_ms,
+            "per_rank_busy_ms": [round(float(v), 2) for v in allst[:, 0]], "per_rank_frames": [int(v) for v in allst[:, 3]],
+            "gather_ms_max": float(allst[:, 1].max()), "imbalance": float(allst[:, 0].max() / allst[:, 0].mean()),
+            "timed_passes": n_timed}
+
+
+def latency_configs(gd, voc):
+    """configs[2] (PNDM-25, 10 s clip) and configs[4] (flask: 0.5 s chunk, PNDM-50) through the public classes with
+    host inputs: wall-clock per call incl. H2D / D2H, synchronised."""
+    from diffsvc_b200.hparams import hparams
+
+    def run(T, speedup, n_calls, warm):
+        hparams["pndm_speedup"] = speedup
+        hub, m2p, f0, f0hz = (t.pin_memory() for t in synth_inputs(1, T, seed=3))
+        out = torch.empty(T * HOP).pin_memory()
+        ts = []
+        for i in range(warm + n_calls):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            ret = gd(hub.cuda(non_blocking=True), m2p.cuda(non_blocking=True), None, None, f0.cuda(non_blocking=True), None, None, infer=True)
+            wav = voc.spec2wav_torch(ret["mel_out"].clamp(-6.0, 1.5), f0=f0hz.cuda(non_blocking=True), seed=i)
+            out.copy_(wav); torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+        return ts
+    try:
+        with torch.no_grad():
+            a = run(862, 40, 10, 3)
+            b = run(43, 20, 100, 5)
+    finally:
+        hparams["pndm_speedup"] = 1
+    return {"cfg2_pndm25_10s": {"latency_ms_p50": statistics.median(a) * 1e3, "audio_sec_per_s": 862 * HOP / SR / statistics.median(a)},
+            "cfg4_flask_0.5s_pndm50": {"latency_ms_p50": statistics.median(b) * 1e3, "latency_ms_p95": sorted(b)[int(0.95 * len(b))] * 1e3,
+                                       "rtf": statistics.median(b) / (43 * HOP / SR)}}
+
+
+def eager_baseline(T):
+    """Second baseline: the reference's modules through STOCK PyTorch eager on this B200
+    (cuDNN / cuBLAS, fp32, TF32 off), same workload, bounded sample (30 DDPM steps + 1 vocoder pass)."""
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = ReferenceCpu(T, 30, device="cuda")
+        if ref.kind != "reference":
+            raise RuntimeError("baseline/_ref absent: no reference modules to run under torch eager")
+        ref.sample()
+        td, tv = ref.sample()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    return {"kind": ref.kind, "ms_per_ddpm_step": td / 30 * 1e3, "vocoder_ms": tv * 1e3,
+            "audio_sec_per_s": (T * HOP / SR) / (td / 30 * 1000 + tv), "note": "30 of 1000 DDPM steps timed, extrapolated; fp32, TF32 off"}
+
+
+def profile_traffic(B, T):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this shape
+    (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture of this shape is committed."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = table.get("conv_gate_B%d_T%d" % (B, T))
+        return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -244,6 +419,7 @@ def main():
         return wav
 
     def timed(fn, n_warm, n_steps, sampler=None):
+        """ms per step (max over ranks of the per-rank sums) and every rank's own ms per step."""
         tot = 0.0
         for i in range(n_warm + n_steps):
             if dist is not None:
@@ -256,24 +432,32 @@ def main():
             torch.cuda.synchronize()
             if i >= n_warm:
                 tot += a.elapsed_time(b)
+        per_rank = [tot / n_steps]
         if dist is not None:
-            t = torch.tensor([tot], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tot = float(t.item())
-        return tot / n_steps     # ms per step, max over ranks
+            t = torch.tensor([tot / n_steps], device="cuda", dtype=torch.float64)
+            every = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_rank = [float(v.item()) for v in every]
+        return max(per_rank), per_rank
 
     with torch.no_grad():
         clk = ClockSampler(local)
         l0 = lib.dsvc_launch_count()
-        ms_dev = timed(step_device, args.warmup, args.steps, clk)
+        ms_dev, ranks_dev = timed(step_device, args.warmup, args.steps, clk)
         clocks = clk.stop()
         launches = (lib.dsvc_launch_count() - l0) // (args.warmup + args.steps) * args.steps
-        ms_e2e = timed(step_e2e, args.warmup, args.steps)
-        # dominant kernel alone: dilated conv + gate of one WaveNet layer (CUDA events on the launch stream)
+        ms_e2e, ranks_e2e = timed(step_e2e, args.warmup, args.steps)
+        # sampler alone, and the two kernels of a layer alone (CUDA events on the launch stream, back to back)
+        ms_sampler, _ = event_ms(lambda: gd.sample(x0_d, cond_d, NS, None, None, seed=3))
         h = gd.denoise_fn.handle()
         it = 200
-        _lib.check(lib.dsvc_diffnet_run_layer(h, 5, 0, 20, _lib.current_stream()))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); _lib.check(lib.dsvc_diffnet_run_layer(h, 5, 0, it, _lib.current_stream())); b.record(); torch.cuda.synchronize()
-        conv_us = a.elapsed_time(b) / it * 1000.0
+        stream = _lib.current_stream()
+
+        def kernel_us(part):
+            _lib.check(lib.dsvc_diffnet_run_layer(h, 5, part, 20, stream))
+            ms, _ = event_ms(lambda: _lib.check(lib.dsvc_diffnet_run_layer(h, 5, part, it, stream)))
+            return ms / it * 1000.0
+        conv_us, out_us = kernel_us(0), kernel_us(1)
 
     audio = world * B * T * HOP / SR
     peaks = {}
@@ -284,33 +468,59 @@ def main():
     peak_burst = float(peaks.get("bf16_tflops", 1590.0))
     peak_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
     conv_tf = FLOP_CONV_PER_FRAME * B * T / conv_us / 1e6
+    out_tf = FLOP_OUT_PER_FRAME * B * T / out_us / 1e6
     sampler_flop = (FLOP_EVAL_PER_FRAME * NS + FLOP_COND_PER_FRAME) * B * T
+    step_us = ms_sampler * 1000.0 / NS
+    L = 20
+    traffic, traffic_src = profile_traffic(B, T)
     line = base_line(args, audio / (ms_dev / 1000.0), ms_dev)
     line.update({
         "dtype": "f32 (fp16 hi/lo split x3 on tcgen05, fp32 accumulate)" if args.math == "tc3f16" else args.math,
         "clocks": clocks, "gpu_launches": int(launches),
+        "per_rank_ms_per_step": [round(v, 3) for v in ranks_dev],
         "e2e": {"value": audio / (ms_e2e / 1000.0), "unit": "audio-sec/s", "ms_per_step": ms_e2e,
+                "per_rank_ms_per_step": [round(v, 3) for v in ranks_e2e],
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_hubert, h_mel2ph, h_f0, h_f0hz))),
                 "d2h_bytes_per_step": int(h_wav.numel() * 4), "api": "GaussianDiffusion.forward + NsfHifiGAN.spec2wav_torch"},
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<EpiGate> (dilated conv + conditioner + gate, one layer)",
                      "achieved": conv_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": conv_tf / peak_burst,
-                     "traffic": 7.54e6 if (B == 1 and T == 862) else None, "us_per_launch": conv_us,
-                     "note": "algorithmic fp32-equivalent FLOPs (2*3*C*2C per frame) / CUDA-event time of the kernel run back to back; "
-                             "the error-compensated fp16 hi/lo split executes 3x those FLOPs on the tensor pipe (ceiling of frac = 0.33). "
-                             "traffic = dram bytes per launch from profiles/r1c_conv_kernel_full.md (ncu --set full; ~= the "
-                             "algorithmic 7.5 MB: weights 3.5 + conditioner 2.6 + activations 1.3). "
-                             "peak = MEASURED_PEAKS.json bf16_tflops (burst)" + ("" if peaks else " [fallback]")},
-        "sampler_flops": {"achieved_tflops": sampler_flop / (ms_dev / 1000.0) / 1e12, "peak_sustained": peak_sus,
-                          "note": "whole step incl. vocoder time; algorithmic DiffNet FLOPs only"},
+                     "frac_executed": PASSES * conv_tf / peak_burst, "frac_ceiling_parity_mode": 1.0 / PASSES,
+                     "audio_sec_per_s_ceiling_parity_mode": peak_burst * 1e12 / PASSES / (FLOP_EVAL_PER_FRAME * NS * SR / HOP),
+                     "traffic": traffic, "traffic_source": traffic_src, "us_per_launch": conv_us,
+                     "note": "achieved = algorithmic fp32-equivalent FLOPs (2*3*C*2C per frame x frames) / CUDA-event time of the kernel "
+                             "run back to back in this process; the error-compensated fp16 hi/lo split executes 3x those FLOPs on the "
+                             "tensor pipe, so frac <= 0.33 and 1000-step DDPM <= ~139 audio-sec/s per B200 in parity mode; "
+                             "traffic = dram bytes per launch read from profiles/traffic.json (ncu --set full of this kernel at this "
+                             "shape), null when no capture of this shape is committed; peak = MEASURED_PEAKS.json bf16_tflops (burst)"
+                             + ("" if peaks else " [fallback]")},
+        "layer_budget": {"conv_gate_us": conv_us, "out_proj_us": out_us, "out_proj_tflops": out_tf,
+                         "ddpm_step_us": step_us, "kernels_per_step": 2 * L + 3,
+                         "boundary_us_per_kernel": (step_us - L * (conv_us + out_us)) / (2 * L + 3),
+                         "note": "ddpm_step_us = 1000-step sampler alone / 1000; boundary = what a step costs beyond its 40 layer "
+                                 "kernels run back to back (hand-overs, head / tail kernels), per kernel"},
+        "sampler_flops": {"achieved_tflops": sampler_flop / (ms_sampler / 1000.0) / 1e12, "peak_sustained": peak_sus,
+                          "frac_of_sustained": sampler_flop / (ms_sampler / 1000.0) / 1e12 / peak_sus,
+                          "note": "algorithmic DiffNet FLOPs of the whole 1000-step sampler / its CUDA-event time"},
     })
-    if rank == 0 and world == 1:      # the CPU baseline is reported at N = 1 only (the other ranks would idle at the barrier)
-        threads = cpu_threads_autotune(sd, T)
-        td, tv = cpu_sample(sd, nsd, T, args.ref_ddpm_sample, seed=5)
+    if not args.no_extras:
+        with torch.no_grad():
+            line["cfg3_sliced_batch"] = cfg3_sliced_batch(gd, voc, dist, rank, world, flush)
+    if rank == 0 and world == 1 and not args.no_extras:
+        # single-GPU legs only: the other ranks would idle at the barrier
+        line["extras"] = latency_configs(gd, voc)
+        try:
+            line["extras"]["torch_eager_b200"] = eager_baseline(T)
+        except Exception as ex:                                      # a baseline, never a reason to lose the bench line
+            line["extras"]["torch_eager_b200"] = {"unavailable": repr(ex)[:200]}
+        ref = ReferenceCpu(T, args.ref_ddpm_sample)
+        threads = ref.autotune_threads()
+        ref.sample()
+        td, tv = ref.sample()
         per_clip = td / args.ref_ddpm_sample * NS + tv
-        line["cpu_baseline"] = {"value": (T * HOP / SR) / per_clip, "unit": "audio-sec/s", "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": (T * HOP / SR) / per_clip, "unit": "audio-sec/s", "cores": threads, "kind": ref.kind,
                                 "sample": "%d of %d DDPM steps (%.2f s) + 1 NSF-HiFiGAN pass (%.2f s) of one %d-frame clip, DDPM part "
-                                          "extrapolated linearly; oracle port of the reference modules, torch CPU fp32, %d threads"
-                                          % (args.ref_ddpm_sample, NS, td, tv, T, threads)}
+                                          "extrapolated linearly; %s, torch CPU fp32, %d threads"
+                                          % (args.ref_ddpm_sample, NS, td, tv, T, _kind_text(ref.kind), threads)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -23,31 +23,45 @@ def partition_slices(lengths: Sequence[int], world_size: int) -> List[List[int]]
     return [sorted(b) for b in bins]
 
 
-def gather_waveforms(local_wavs: List[torch.Tensor], local_ids: List[int], n_total: int, group=None) -> List[torch.Tensor]:
-    """All-gather variable-length waveforms: lengths first, then one padded payload exchange.
-    Returns the full job's waveforms in slice order on every rank."""
+def gather_waveforms(local_wavs: List[torch.Tensor], local_ids: List[int], n_total: int, group=None,
+                     device=None) -> List[torch.Tensor]:
+    """All-gather variable-length waveforms: one small metadata exchange (slice id, samples), then ONE padded
+    payload exchange.  Returns the full job's waveforms in slice order on every rank.
+
+    `device`: where the collective's buffers live.  Default: the local waveforms' device, else the current CUDA
+    device under the NCCL backend (a rank that received no slice must still join the collective with CUDA
+    tensors), else the CPU (gloo)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    dev = local_wavs[0].device if local_wavs else torch.device("cpu")
-    meta = torch.full((n_total, 2), -1, dtype=torch.int64, device=dev)        # per local slot: (slice id, samples)
+    if device is None:
+        if local_wavs:
+            device = local_wavs[0].device
+        elif dist.get_backend(group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            device = torch.device("cpu")
+    meta = torch.full((n_total, 2), -1, dtype=torch.int64)               # per local slot: (slice id, samples)
     for k, (i, w) in enumerate(zip(local_ids, local_wavs)):
-        meta[k, 0], meta[k, 1] = i, w.numel()
-    metas = [torch.empty_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    max_total = max(int(m[:, 1].clamp(min=0).sum()) for m in metas)
-    payload = torch.zeros(max(max_total, 1), dtype=torch.float32, device=dev)
+        meta[k, 0], meta[k, 1] = int(i), int(w.numel())
+    meta = meta.to(device)
+    metas = torch.empty((world * n_total, 2), dtype=torch.int64, device=device)     # concatenated along dim 0
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas = metas.view(world, n_total, 2).cpu()                                                  # the one host sync: payload sizes
+    max_total = int(metas[:, :, 1].clamp(min=0).sum(dim=1).max())
+    payload = torch.zeros(max(max_total, 1), dtype=torch.float32, device=device)
     if local_wavs:
-        flat = torch.cat([w.reshape(-1).to(torch.float32) for w in local_wavs])
+        flat = torch.cat([w.reshape(-1).to(device=device, dtype=torch.float32) for w in local_wavs])
         payload[:flat.numel()] = flat
-    payloads = [torch.empty_like(payload) for _ in range(world)]
-    dist.all_gather(payloads, payload, group=group)
+    payloads = torch.empty(world * payload.numel(), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(payloads, payload, group=group)
+    payloads = payloads.view(world, payload.numel())
     out = [None] * n_total
-    for m, p in zip(metas, payloads):
+    for r in range(world):
         off = 0
-        for i, n in m.tolist():
+        for i, n in metas[r].tolist():
             if i < 0:
                 continue
-            out[i] = p[off:off + n].clone()
+            out[i] = payloads[r, off:off + n].clone()
             off += n
     assert all(o is not None for o in out), "a slice was not produced by any rank"
     return out

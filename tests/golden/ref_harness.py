@@ -23,7 +23,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DIFFSVC_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the unmodified copy that `__graft_entry__.build()`
+    left under baseline/_ref (git-ignored, shipped by gpurun like the built .so files)."""
+    env = os.environ.get("DIFFSVC_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO_ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "network", "diff")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 _STUBS = [
     "librosa", "librosa.filters", "librosa.util", "librosa.core", "pycwt", "matplotlib", "matplotlib.pylab",

@@ -38,12 +38,11 @@ def _worker(rank, world, port, lengths, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_gather_gloo():
-    lengths = [7, 3, 11, 5, 2]
+def _run(lengths, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lengths, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -53,3 +52,13 @@ def test_two_rank_gather_gloo():
     for rank, ok, sizes in res:
         assert ok, rank
         assert sizes == [n * 4 for n in lengths]
+
+
+def test_two_rank_gather_gloo():
+    _run([7, 3, 11, 5, 2])
+
+
+def test_gather_with_an_empty_rank():
+    """n_slices < world_size: partition_slices leaves a rank without work; it must still join both collectives."""
+    _run([9], world=2)
+    _run([4, 6], world=3)

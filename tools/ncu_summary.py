@@ -2,6 +2,9 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md
   python tools/ncu_summary.py kernel   gpurun_out/prof_conv_r1.ncu-rep profiles/r1_conv_kernel.md
+  python tools/ncu_summary.py traffic  gpurun_out/prof_conv_r2.ncu-rep conv_gate_B1_T862 EpiGate profiles/r2_conv_kernel_full.md
+        (records dram bytes per launch of the kernels matching <substring> in profiles/traffic.json, which
+         bench.py reads for roofline.traffic)
 """
 import collections
 import csv
@@ -58,5 +61,33 @@ def kernel(src, dst):
             f.write("\n")
 
 
+def traffic(src, key, match, cite):
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for r in rows[2:]:
+        if match not in r[hdr.index("Kernel Name")]:
+            continue
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        vals.append(tot)
+    assert vals, "no kernel matching %r in %s" % (match, src)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    table = json.load(open(path)) if os.path.exists(path) else {}
+    table[key] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals),
+                  "source": "%s (ncu --set full, kernels matching '%s', dram__bytes_read.sum + dram__bytes_write.sum)" % (cite, match)}
+    json.dump(table, open(path, "w"), indent=2)
+    print(key, table[key])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:6])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
