@@ -129,19 +129,21 @@ class ReferenceCpu:
         self.sd, self.nsd = S.synth_diffnet_weights(), S.synth_nsf_weights(S.NSF_H_44K)
         self.kind = "reference" if os.path.isdir(os.path.join(REF_DIR, "network", "diff")) else "port"
         if self.kind == "reference":
+            import contextlib
             os.environ["DIFFSVC_REFERENCE_ROOT"] = REF_DIR
             sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
             import ref_harness as rh
-            hp = rh.install()
-            diffusion, net = rh.import_diffusion()
-            models = rh.import_nsf_models()
-            from modules.nsf_hifigan.env import AttrDict
-            self.gd = diffusion.GaussianDiffusion(None, MEL, net.DiffNet(MEL), timesteps=1000, K_step=n_ddpm, loss_type="l2",
-                                                  spec_min=[-5.0], spec_max=[0.0]).eval()
-            self.gd.denoise_fn.load_state_dict(self.sd, strict=True)
-            self.gen = models.Generator(AttrDict(S.NSF_H_44K)).eval()
-            self.gen.remove_weight_norm()
-            self.gen.load_state_dict(self.nsd)
+            with contextlib.redirect_stdout(sys.stderr):             # the reference prints while it builds: keep stdout = ONE JSON line
+                hp = rh.install()
+                diffusion, net = rh.import_diffusion()
+                models = rh.import_nsf_models()
+                from modules.nsf_hifigan.env import AttrDict
+                self.gd = diffusion.GaussianDiffusion(None, MEL, net.DiffNet(MEL), timesteps=1000, K_step=n_ddpm, loss_type="l2",
+                                                      spec_min=[-5.0], spec_max=[0.0]).eval()
+                self.gd.denoise_fn.load_state_dict(self.sd, strict=True)
+                self.gen = models.Generator(AttrDict(S.NSF_H_44K)).eval()
+                self.gen.remove_weight_norm()
+                self.gen.load_state_dict(self.nsd)
             self.gd.to(device); self.gen.to(device)
             hp["pndm_speedup"] = 1
         else:
@@ -167,7 +169,9 @@ class ReferenceCpu:
         for n in sorted({min(ncpu, k) for k in (8, 16, 32, 64, ncpu)}):
             torch.set_num_threads(n)
             self.eval_once()
-            t0 = time.perf_counter(); self.eval_once(); dt = time.perf_counter() - t0
+            dt = 1e9
+            for _ in range(3):                                       # best of 3: one noisy eval must not pick the thread count
+                t0 = time.perf_counter(); self.eval_once(); dt = min(dt, time.perf_counter() - t0)
             if best is None or dt < best[1]:
                 best = (n, dt)
         torch.set_num_threads(best[0])
@@ -496,8 +500,10 @@ def main():
         "layer_budget": {"conv_gate_us": conv_us, "out_proj_us": out_us, "out_proj_tflops": out_tf,
                          "ddpm_step_us": step_us, "kernels_per_step": 2 * L + 3,
                          "boundary_us_per_kernel": (step_us - L * (conv_us + out_us)) / (2 * L + 3),
-                         "note": "ddpm_step_us = 1000-step sampler alone / 1000; boundary = what a step costs beyond its 40 layer "
-                                 "kernels run back to back (hand-overs, head / tail kernels), per kernel"},
+                         "note": "conv_gate_us / out_proj_us = launch-to-launch period of one kernel repeated back to back (so each "
+                                 "includes one kernel boundary: drain, dependent release, first operand tiles); ddpm_step_us = 1000-step "
+                                 "sampler alone / 1000; boundary_us_per_kernel = what a step costs beyond 20 x (conv + out-proj) periods, "
+                                 "spread over its 43 kernels (head / tail kernels, the conv <-> out-proj alternation)"},
         "sampler_flops": {"achieved_tflops": sampler_flop / (ms_sampler / 1000.0) / 1e12, "peak_sustained": peak_sus,
                           "frac_of_sustained": sampler_flop / (ms_sampler / 1000.0) / 1e12 / peak_sus,
                           "note": "algorithmic DiffNet FLOPs of the whole 1000-step sampler / its CUDA-event time"},

@@ -3,7 +3,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
-#include "tc_gemm.cuh"
+#include "tc_pair.cuh"
 #include "tc_splitk.cuh"
 #include "tc_layer.cuh"
 
@@ -120,6 +120,8 @@ struct dsvc_diffnet {
   bool pingpong = false; // Y / Y2 alternate by layer parity: a layer's out-proj never overwrites the plane its conv reads
   int fused_usable = 0;  // how many clusters of 2C/64 CTAs of tc_layer_kernel fit the device at once (probed in prepare; 0: none)
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
+  DevBuf tile_tab;       // ragged batches: (item, first frame) of every frame tile with a valid frame, dead slots (0,-1) behind
+  int tile_slots = 0, tile_live = 0;   // 0 slots: dense grid (all items full length)
   DevBuf sk_slab;        // split-K partial tiles [B][m_tiles][n_tiles][3][128][128] fp32 (tc_splitk.cuh)
   int num_sms = 148;
   // CUDA graphs of one sampler step
@@ -137,6 +139,12 @@ struct dsvc_diffnet {
 };
 
 namespace dsvc {
+
+static TcTiles tiles_of(const dsvc_diffnet* h) {
+  TcTiles t;
+  if (h->tile_slots > 0) { t.tab = h->tile_tab.as<int2>(); t.slots = h->tile_slots; t.live = h->tile_live; }
+  return t;
+}
 
 static int upload_f(DevBuf& b, const std::vector<float>& v, cudaStream_t s) {
   return b.upload(v.data(), v.size() * sizeof(float), s);
@@ -324,10 +332,14 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
   if (h->tc) {
     const TcGemmMaps& m = h->maps.dil[l];
     // grids that leave SMs idle (one clip): one tap per CTA in a 3-CTA cluster, reduced through an L2 slab
-    if (h->passes == 3 && h->sk_slab.bytes >= tc_splitk_slab_bytes(B, T, 2 * C) &&
+    // (measured, 43 frames: CTA pairs 295 us per step, split-K + pairs 316, split-K + single-CTA kernels 328 -- so the
+    //  split is automatic only next to the single-CTA kernels, and on request: DSVC_SPLITK >= 1)
+    const char* skv = getenv("DSVC_SPLITK");
+    const bool sk_wanted = (skv && atoi(skv) >= 1) || !tc_pair_enabled();
+    if (h->passes == 3 && sk_wanted && h->tile_slots == 0 && h->sk_slab.bytes >= tc_splitk_slab_bytes(B, T, 2 * C) &&
         tc_splitk_eligible(B, T, 2 * C, 3, h->num_sms))
       return tc_splitk_launch<EpiGate>(m, e, h->sk_slab.as<float>(), B, T, C, 2 * C, dil, s);
-    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s);
+    return tc_launch<EpiGate>(m, e, B, T, C, 2 * C, 3, dil, h->passes, s, tiles_of(h));
   }
   const float* W = h->w_dil.as<float>() + (size_t)l * 3 * 2 * C * C;
   return launch_fp32<EpiGate>(h, base_params(h->Y.f32.as<float>(), W, B, T, C, 2 * C, 3, dil), e, s);
@@ -337,7 +349,7 @@ static int enqueue_layer_conv(dsvc_diffnet* h, int l, cudaStream_t s) {
 static int enqueue_layer_out(dsvc_diffnet* h, int l, int tsel, cudaStream_t s) {
   const int C = h->cfg.residual_channels, B = h->B, T = h->Tmax;
   const EpiOutProj::Params e = mk_outproj(h, l, tsel);
-  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s);
+  if (h->tc) return tc_launch<EpiOutProj>(h->maps.out[l], e, B, T, C, 2 * C, 1, 0, h->passes, s, tiles_of(h));
   const float* W = h->w_out.as<float>() + (size_t)l * 2 * C * C;
   return launch_fp32<EpiOutProj>(h, base_params(h->Z.f32.as<float>(), W, B, T, C, 2 * C, 1, 0), e, s);
 }
@@ -352,6 +364,7 @@ static int enqueue_layer_fused(dsvc_diffnet* h, int l, int tsel, cudaStream_t s)
 }
 
 static bool fused_layers(const dsvc_diffnet* h) {
+  if (h->tile_slots > 0) return false;     // ragged batches run from the tile table
   if (!(h->tc && h->pingpong && h->fused_usable >= 1 &&
         tc_layer_shape_ok(h->B, h->Tmax, h->cfg.residual_channels))) return false;
   // automatic mode: only while every frame tile's cluster is resident at once (a second wave of clusters doubles the layer)
@@ -364,7 +377,7 @@ static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
   const int B = h->B, T = h->Tmax;
   {  // K0 input_projection + ReLU
     const EpiInProj::Params e = mk_inproj(h, ha.tsel);
-    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s, tiles_of(h)));
     else DSVC_TRY(launch_fp32<EpiInProj>(h, base_params(h->XIN.f32.as<float>(), h->w_in.as<float>(), B, T, M, C, 1, 0), e, s));
   }
   for (int l = 0; l < L; ++l) {
@@ -377,12 +390,12 @@ static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
   }
   {  // K4a skip_projection + ReLU
     const EpiSkipProj::Params e = mk_skip(h);
-    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiSkipProj>(h->maps.skip, e, B, T, C, C, 1, 0, h->passes, s, tiles_of(h)));
     else DSVC_TRY(launch_fp32<EpiSkipProj>(h, base_params(h->SP.f32.as<float>(), h->w_skip.as<float>(), B, T, C, C, 1, 0), e, s));
   }
   {  // K4b output_projection + sampler update
     const EpiHead::Params e = mk_head(h, ha);
-    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s));
+    if (h->tc) DSVC_TRY(tc_launch<EpiHead>(h->maps.head, e, B, T, C, M, 1, 0, h->passes, s, tiles_of(h)));
     else DSVC_TRY(launch_fp32<EpiHead>(h, base_params(h->R.f32.as<float>(), h->w_head.as<float>(), B, T, C, M, 1, 0), e, s));
   }
   return DSVC_OK;
@@ -516,8 +529,31 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
   DSVC_TRY(h->R.reserve(n * C, tc));
   DSVC_TRY(h->XIN.reserve(n * M, tc));
   DSVC_CUDA(cudaMemcpyAsync(h->lengths.p, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  DSVC_CUDA(cudaStreamSynchronize(s));   // `len` is a stack-owned staging buffer
-  if (resized || !h->prepared) {
+  // Ragged batch on the tensor-core path: only the frame tiles that hold a valid frame do work.  The grid keeps the
+  // dense size (a captured graph stays valid whatever the lengths are); dead slots exit at once.  Frames beyond an
+  // item's length are then never written, so the conv-input planes -- whose rows just past the end ARE read, as the
+  // zero padding of the item's last frames -- are cleared here once.
+  std::vector<int2> tab;
+  const int dense = B * ceil_div(Tmax, TC_BM);
+  if (tc) {
+    for (int b = 0; b < B; ++b)
+      for (int m0 = 0; m0 < len[b]; m0 += TC_BM) tab.push_back(make_int2(b, m0));
+  }
+  const bool ragged = tc && (int)tab.size() < dense;
+  const bool ragged_changed = ragged != (h->tile_slots > 0);
+  if (ragged) {
+    h->tile_live = (int)tab.size();
+    h->tile_slots = 2 * ceil_div(dense, 2);
+    tab.resize(h->tile_slots, make_int2(0, -1));
+    DSVC_TRY(h->tile_tab.reserve(tab.size() * sizeof(int2)));
+    DSVC_CUDA(cudaMemcpyAsync(h->tile_tab.p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    DSVC_CUDA(cudaMemsetAsync(h->Y.hi.p, 0, n * C * sizeof(__half), s));
+    DSVC_CUDA(cudaMemsetAsync(h->Y.lo.p, 0, n * C * sizeof(__half), s));
+  } else {
+    h->tile_slots = h->tile_live = 0;
+  }
+  DSVC_CUDA(cudaStreamSynchronize(s));   // `len` / `tab` are stack-owned staging buffers
+  if (resized || !h->prepared || ragged_changed) {
     h->g_ddpm_valid = h->g_plms_valid = false;
     if (tc) DSVC_TRY(tc_build_maps(h));
   }

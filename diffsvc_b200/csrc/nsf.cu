@@ -8,7 +8,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
-#include "tc_gemm.cuh"
+#include "tc_pair.cuh"
 
 #include <memory>
 

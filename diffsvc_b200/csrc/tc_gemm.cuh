@@ -43,6 +43,14 @@ struct TcMaps {
   std::vector<TcGemmMaps> dil, out;
 };
 
+// Ragged batches: the frame tiles that hold at least one valid frame, as (item, first frame) entries; the grid's x
+// axis indexes this table instead of (frame tile, item).  `slots` (the grid size: the dense tile count, so a captured
+// graph does not depend on the lengths) >= `live`; the entries past `live` are (0, -1) and their CTAs exit at once.
+struct TcTiles {
+  const int2* tab = nullptr;
+  int slots = 0, live = 0;
+};
+
 struct F16Pair {           // tcgen05 operand: fp16 hi/lo copies of a (power-of-two scaled) weight matrix
   DevBuf hi, lo;
   float inv_scale = 1.f;   // multiply the accumulator by this in the epilogue
@@ -237,6 +245,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
 #ifdef DSVC_TIMELINE
                                             , long long tl0, int tl_off = 0
 #endif
+                                            , int pair_h = 0   // tc_pair.cuh accumulator layout: channel j adds column j + (j < h ? 3h : h)
 ) {
 #ifndef DSVC_TIMELINE
     constexpr int tl_off = 0;
@@ -318,7 +327,8 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
         tmem_ld_cols<LW>(taddr, v);
         if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
           float v2[LW];
-          tmem_ld_cols<LW>(taddr + (uint32_t)BN, v2);
+          const uint32_t partner = pair_h == 0 ? (uint32_t)BN : (uint32_t)((cg * CW + c0) < pair_h ? 3 * pair_h : pair_h);
+          tmem_ld_cols<LW>(taddr + partner, v2);
 #pragma unroll
           for (int j = 0; j < LW; ++j) v[j] += v2[j];
         }
@@ -370,11 +380,17 @@ template <class Epi, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes) {
+               const typename Epi::Params ep, int T, int K, int N, int taps, int dil, int passes, const int2* __restrict__ tiles) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   pdl_launch_dependents();                   // let the next kernel's prologue start early
+  int m0 = blockIdx.x * TC_BM, b = blockIdx.z;
+  if (tiles != nullptr) {                    // ragged batch: (item, first frame) of this CTA's tile; dead slots leave
+    const int2 t = __ldg(tiles + blockIdx.x);
+    if (t.y < 0) return;
+    b = t.x; m0 = t.y;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE;
@@ -390,7 +406,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #ifdef DSVC_TIMELINE
   const long long tl0 = clock64();
 #endif
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const int n0 = blockIdx.y * BN;
   const int kblocks = K / TC_BK;
   const int total = taps * kblocks;
   const bool three = passes == 3;
@@ -602,10 +618,10 @@ static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, in
 
 template <class Epi, int BN>
 int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-                 cudaStream_t s) {
+                 cudaStream_t s, TcTiles tt = TcTiles{}) {
   DSVC_TRY((ensure_dyn_smem<tc_gemm_kernel<Epi, BN>>(TcCfg<BN>::SMEM)));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ceil_div(T, TC_BM), ceil_div(N, BN), B);
+  cfg.gridDim = tt.tab ? dim3(tt.slots, ceil_div(N, BN), 1) : dim3(ceil_div(T, TC_BM), ceil_div(N, BN), B);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
   cfg.stream = s;
@@ -617,7 +633,7 @@ int tc_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int 
   const bool b64 = (BN == 256) && Epi::kPair;
   const CUtensorMap& bh = (BN == 64) ? m.b32_hi : (b64 ? m.b64_hi : m.b_hi);
   const CUtensorMap& bl = (BN == 64) ? m.b32_lo : (b64 ? m.b64_lo : m.b_lo);
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi, BN>, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, passes));
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi, BN>, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, passes, tt.tab));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }
@@ -630,39 +646,41 @@ inline int tc_forced_bn() {
 
 // 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
 // 1.7+ waves the narrower tiles re-fetch the activation tile twice as often and lose ~35 %)
-inline bool tc_narrow_tiles(int B, int T, int N) {
+inline bool tc_narrow_tiles(long long mtiles, int N) {
   const int forced = tc_forced_bn();
   if (forced == 64) return true;
   if (forced == 128) return false;
-  return (long long)ceil_div(T, TC_BM) * ceil_div(N, 128) * B < 148;
+  return mtiles * ceil_div(N, 128) < 148;
 }
 
 // 256-wide tiles (best operand reuse: ~235 vs 281 smem bytes per column per K-step) once they fill the GPU
-inline bool tc_wide_tiles(int B, int T, int N) {
+inline bool tc_wide_tiles(long long mtiles, int N) {
   const int forced = tc_forced_bn();
   if (N % 256 != 0) return false;
   if (forced == 256) return true;
   if (forced == 64 || forced == 128) return false;
-  return (long long)ceil_div(T, TC_BM) * (N / 256) * B >= 120;
+  return mtiles * (N / 256) >= 120;
 }
 
 // tile width the launcher will pick, and the resulting CTAs per (item, frame tile)
-inline int tc_pick_bn(int B, int T, int N) {
+// (mtiles: frame tiles that do work -- the live entries of a ragged batch's tile table, else B * ceil(T / 128))
+inline int tc_pick_bn(int B, int T, int N, int live_tiles = 0) {
+  const long long mtiles = live_tiles > 0 ? live_tiles : (long long)ceil_div(T, TC_BM) * B;
   if (N % 128 != 0 && N % 64 == 0) return 64;        // a 128-wide tile would be half empty
-  if (tc_narrow_tiles(B, T, N) && N % 64 == 0) return 64;
-  if (tc_wide_tiles(B, T, N)) return 256;
+  if (tc_narrow_tiles(mtiles, N) && N % 64 == 0) return 64;
+  if (tc_wide_tiles(mtiles, N)) return 256;
   return 128;
 }
 inline int tc_ctas_per_mtile(int B, int T, int N) { return ceil_div(N, tc_pick_bn(B, T, N)); }
 
 template <class Epi>
-int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-              cudaStream_t s) {
+int tc_launch_single(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
+                     cudaStream_t s, TcTiles tt = TcTiles{}) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
-  const int bn = tc_pick_bn(B, T, N);
-  if (bn == 64) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s);
-  if (bn == 256) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s);
-  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s);
+  const int bn = tc_pick_bn(B, T, N, tt.live);
+  if (bn == 64) return tc_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, passes, s, tt);
+  if (bn == 256) return tc_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, passes, s, tt);
+  return tc_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, passes, s, tt);
 }
 
 }  // namespace dsvc

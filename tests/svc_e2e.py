@@ -110,18 +110,26 @@ def make(workdir, seconds, k_step, seed=1234):
     np.save(os.path.join(workdir, "raw", "clip.npy"), (torch.randn(n_units, 256, generator=g) * 0.5).numpy())
 
 
+def _soundfile_double():
+    """`soundfile` is absent from this image and ref_harness stubs it; give the stub a working `read` (scipy's wav
+    reader) -- both the reference's loader (nvSTFT.py:17) and ours prefer soundfile when it is importable."""
+    from scipy.io import wavfile
+    sf = sys.modules.get("soundfile")
+    if sf is None or hasattr(sf, "__file__"):
+        return                                   # the real library is installed: nothing to do
+
+    def read(path, always_2d=True, **kw):
+        rate, data = wavfile.read(path)
+        return (data.reshape(len(data), -1) if always_2d else data), rate
+    sf.read = read
+
+
 def _shim_reference_host_libs(torch):
     """Third-party pieces the reference's wav2spec needs that this image lacks or has moved on from (none of it is
     reference code): soundfile.read -> scipy's wav reader, librosa.filters.mel -> the oracle's restatement of the
     published Slaney filterbank, torch.stft without return_complex (torch 1.12 semantics, requirements.txt:90)."""
-    from scipy.io import wavfile
     import modules.nsf_hifigan.nvSTFT as nv
     from oracle import diffsvc_oracle as O
-
-    def sf_read(path, always_2d=True):
-        rate, data = wavfile.read(path)
-        return (data.reshape(len(data), -1) if always_2d else data), rate
-    nv.sf.read = sf_read
     nv.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: O.slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)
     stft_now = torch.stft
 
@@ -156,6 +164,7 @@ def run(workdir, arm, acc, use_pe, patch_after_infer, out, draws_in):
     import torch
     import ref_harness as rh
     rh.install()
+    _soundfile_double()
     if arm == "native":
         assert torch.cuda.is_available()
         import diffsvc_b200.dropin as dropin
@@ -178,6 +187,12 @@ def run(workdir, arm, acc, use_pe, patch_after_infer, out, draws_in):
         assert type(svc.pe).__module__.startswith("diffsvc_b200"), type(svc.pe)
     captured = {}
     kwargs = {}
+    orig_out2mel = svc.model.out2mel
+
+    def out2mel(x):                                # the denoised mel BEFORE after_infer's clip: its range scales the gate
+        captured["mel_absmax"] = np.array(float(x.detach().abs().max().cpu()))
+        return orig_out2mel(x)
+    svc.model.out2mel = out2mel
     k_step = int(hparams["K_step"])
     if arm == "native":
         g = torch.Generator().manual_seed(99)

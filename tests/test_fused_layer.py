@@ -18,6 +18,13 @@ pytestmark = [pytest.mark.gpu,
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _single_cta_kernels(monkeypatch):
+    """Bit-identity is stated against the single-CTA kernels (tc_gemm.cuh): the CTA-pair kernels of the default path
+    (tc_pair.cuh) add the three partial products of half the channels in another order."""
+    monkeypatch.setenv("DSVC_TC_PAIR", "0")
+
+
 def _model(K_step=1000):
     import diffsvc_b200 as D
     from diffsvc_b200.hparams import hparams, DEFAULTS_44K
