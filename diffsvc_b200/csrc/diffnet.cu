@@ -621,7 +621,7 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
     static long long host_tl[1024][16];
     DSVC_CUDA(cudaStreamSynchronize(s));
     DSVC_CUDA(cudaMemcpyFromSymbol(host_tl, g_timeline, sizeof(host_tl)));
-    const int nct = ceil_div(h->Tmax, TC_BM) * ceil_div(2 * h->cfg.residual_channels, 64) * h->B;
+    const int nct = 2 * ceil_div(ceil_div(h->Tmax, TC_BM), 2) * ceil_div(2 * h->cfg.residual_channels, 64) * h->B;
     if (part == 2) {
       printf("timeline fused layer (cycles since CTA entry): setup | A:first-operands | A:mma-issued | A:epi-prefetch | A:acc-ready | "
              "A:staged | A:epi-done | fences | cluster-barrier | B:first-operands | B:mma-issued | B:epi-prefetch | B:acc-ready | "
@@ -631,10 +631,13 @@ int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32
                host_tl[c][0], host_tl[c][1], host_tl[c][2], host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6], host_tl[c][7],
                host_tl[c][8], host_tl[c][9], host_tl[c][10], host_tl[c][11], host_tl[c][12], host_tl[c][13], host_tl[c][14]);
     } else {
-    printf("timeline part %d (cycles since CTA entry): setup | first-operands | mma-issued | epi-prefetch | acc-ready | staged | epi-done\n", part);
-    for (int c = 0; c < nct && c < 1024; c += (nct > 12 ? nct / 12 : 1))
-      printf("  cta %3d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, host_tl[c][0], host_tl[c][1], host_tl[c][2],
-             host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6]);
+    long long e0 = host_tl[0][15];
+    for (int c = 0; c < nct && c < 1024; ++c) e0 = host_tl[c][15] < e0 ? host_tl[c][15] : e0;
+    printf("timeline part %d (cycles since CTA entry): setup | first-operands | mma-issued | epi-prefetch | acc-ready | staged | epi-done"
+           " || CTA entry, ns after the first CTA of the last launch (globaltimer)\n", part);
+    for (int c = 0; c < nct && c < 1024; c += (nct > 24 ? nct / 24 : 1))
+      printf("  cta %3d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld || %7lld\n", c, host_tl[c][0], host_tl[c][1], host_tl[c][2],
+             host_tl[c][3], host_tl[c][4], host_tl[c][5], host_tl[c][6], host_tl[c][15] - e0);
     }
     fflush(stdout);
   }

@@ -253,7 +253,7 @@ struct ConvW {
   // tcgen05 path (ResBlock convs whose channel count tiles by 64): fp16 hi/lo weights [K][Cout][Cin] + their TMA maps
   bool tc = false;
   F16Pair h16;
-  CUtensorMap bh, bl, b32h, b32l;
+  CUtensorMap bh, bl, b32h, b32l, b64h, b64l;   // weight boxes of 128 / 32 / 64 rows (tc_gemm.cuh, tc_pair.cuh)
 };
 
 // x -> fp16 (hi, lo) planes of leaky_relu(x): the operand of the first conv of every ResBlock of a stage
@@ -309,6 +309,8 @@ static int upload_conv(ConvW& c, const float* w, const float* b, int Cout, int C
     DSVC_TRY(tc_make_b_map(&c.bl, c.h16.lo.as<__half>(), K * Cout, Cin, 128));
     DSVC_TRY(tc_make_b_map(&c.b32h, c.h16.hi.as<__half>(), K * Cout, Cin, 32));
     DSVC_TRY(tc_make_b_map(&c.b32l, c.h16.lo.as<__half>(), K * Cout, Cin, 32));
+    DSVC_TRY(tc_make_b_map(&c.b64h, c.h16.hi.as<__half>(), K * Cout, Cin, 64));
+    DSVC_TRY(tc_make_b_map(&c.b64l, c.h16.lo.as<__half>(), K * Cout, Cin, 64));
   } else {
     DSVC_TRY(c.w.upload(r.data(), r.size() * 4, s));
   }
@@ -366,7 +368,7 @@ static int conv_same(const ConvW& c, const float* in, float* out, const float* r
 // the same convolution on the tcgen05 path: `in` are the TMA maps of the (already leaky_relu'ed) operand planes
 static int conv_same_tc(const ConvW& c, const TcGemmMaps& in, EpiVoc::Params e, int B, int L, int dil, cudaStream_t s) {
   TcGemmMaps g = in;
-  g.b_hi = c.bh; g.b_lo = c.bl; g.b32_hi = c.b32h; g.b32_lo = c.b32l;
+  g.b_hi = c.bh; g.b_lo = c.bl; g.b32_hi = c.b32h; g.b32_lo = c.b32l; g.b64_hi = c.b64h; g.b64_lo = c.b64l;
   e.bias = c.b.as<float>(); e.Lout = L; e.Cout = c.Cout; e.wscale = c.h16.inv_scale;
   return tc_launch<EpiVoc>(g, e, B, L, c.Cin, c.Cout, c.K, dil, 3, s);
 }

@@ -233,8 +233,12 @@ template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, flo
 #ifdef DSVC_TIMELINE
 __device__ long long g_timeline[1024][16];
 #define TL_MARK(slot) do { if (lane == 0) g_timeline[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 1023][slot] = clock64() - tl0; } while (0)
+// slot 15: %globaltimer (ns) at CTA entry -- the one clock all CTAs share: orders early (pre-launched) and late CTAs
+#define TL_ENTRY() do { if (threadIdx.x == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+  g_timeline[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 1023][15] = (long long)gt_; } } while (0)
 #else
 #define TL_MARK(slot) do { } while (0)
+#define TL_ENTRY() do { } while (0)
 #endif
 
 // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
@@ -405,6 +409,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef DSVC_TIMELINE
   const long long tl0 = clock64();
+  TL_ENTRY();
 #endif
   const int n0 = blockIdx.y * BN;
   const int kblocks = K / TC_BK;
@@ -644,32 +649,35 @@ inline int tc_forced_bn() {
   return e ? atoi(e) : -1;
 }
 
-// 64-wide tiles only when 128-wide ones would not even fill one wave of the 148 SMs (measured: at
-// 1.7+ waves the narrower tiles re-fetch the activation tile twice as often and lose ~35 %)
-inline bool tc_narrow_tiles(long long mtiles, int N) {
-  const int forced = tc_forced_bn();
-  if (forced == 64) return true;
-  if (forced == 128) return false;
-  return mtiles * ceil_div(N, 128) < 148;
-}
-
-// 256-wide tiles (best operand reuse: ~235 vs 281 smem bytes per column per K-step) once they fill the GPU
-inline bool tc_wide_tiles(long long mtiles, int N) {
-  const int forced = tc_forced_bn();
-  if (N % 256 != 0) return false;
-  if (forced == 256) return true;
-  if (forced == 64 || forced == 128) return false;
-  return mtiles * (N / 256) >= 120;
-}
-
-// tile width the launcher will pick, and the resulting CTAs per (item, frame tile)
+// Tile width: the one that minimises  waves x (time of one CTA of that width),  waves = ceil(CTAs / SMs).  Relative CTA
+// times measured with the layer kernels on a B200 (profiles/r2a_pair_vs_single_ab.txt: one clip, 64-wide tiles, conv
+// kernel 9.4 us; 8 clips, 256-wide tiles, one wave, 25.4 us; 128-wide tiles, two waves, 29.5 us):  64: 0.37,
+// 128: 0.56, 256: 1.  One 10 s clip -> 64 (96 CTAs, one wave); 8 x 689 frames -> 256 (144 CTAs, one wave); a ragged batch
+// whose live tiles just miss one wave of 256-wide tiles (e.g. 50 x 3 = 150 CTAs) -> 128 instead of two waves of 256.
 // (mtiles: frame tiles that do work -- the live entries of a ragged batch's tile table, else B * ceil(T / 128))
 inline int tc_pick_bn(int B, int T, int N, int live_tiles = 0) {
   const long long mtiles = live_tiles > 0 ? live_tiles : (long long)ceil_div(T, TC_BM) * B;
+  const int forced = tc_forced_bn();
+  if (forced == 64 && N % 64 == 0) return 64;
+  if (forced == 256 && N % 256 == 0) return 256;
+  if (forced == 128 || forced == 256 || forced == 64) return (N % 128 != 0 && N % 64 == 0) ? 64 : 128;
   if (N % 128 != 0 && N % 64 == 0) return 64;        // a 128-wide tile would be half empty
-  if (tc_narrow_tiles(mtiles, N) && N % 64 == 0) return 64;
-  if (tc_wide_tiles(mtiles, N)) return 256;
-  return 128;
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int widths[3] = {64, 128, 256};
+  const double cost[3] = {0.37, 0.56, 1.0};
+  int best = 128;
+  double best_t = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    if (N % widths[i] != 0) continue;
+    const long long ctas = mtiles * (N / widths[i]);
+    const double t = (double)((ctas + sms - 1) / sms) * cost[i];
+    if (t < best_t - 1e-9) { best_t = t; best = widths[i]; }      // ties: the narrower tile (more SMs busy, shorter chain)
+  }
+  return best;
 }
 inline int tc_ctas_per_mtile(int B, int T, int N) { return ceil_div(N, tc_pick_bn(B, T, N)); }
 

@@ -106,6 +106,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef DSVC_TIMELINE
   const long long tl0 = clock64();
+  TL_ENTRY();
 #endif
   const uint32_t rank = cluster_ctarank();       // 0 = even CTA (issues the MMAs), 1 = odd
   const int kblocks = K / TC_BK;

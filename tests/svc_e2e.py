@@ -220,8 +220,9 @@ def run(workdir, arm, acc, use_pe, patch_after_infer, out, draws_in):
                 rand_ini = torch.rand(1, 9, generator=g)
                 sine_noise = torch.randn(1, n * 512, 9, generator=g)
                 draws.append(("rand", rand_ini.numpy())); draws.append(("randn", sine_noise.numpy()))
-                captured["mel_pred"] = mel.detach().cpu().numpy() if hasattr(mel, "detach") else np.asarray(mel)
-                captured["f0_voc"] = kw["f0"].detach().cpu().numpy() if hasattr(kw.get("f0"), "detach") else np.asarray(kw.get("f0") if "f0" in kw else a[0])
+                to_np = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+                captured["mel_pred"] = to_np(mel)
+                captured["f0_voc"] = to_np(kw["f0"] if "f0" in kw else a[0])
                 return orig(mel, *a, rand_ini=rand_ini, sine_noise=sine_noise, **kw)
             setattr(svc.vocoder, fn_name, call)
         wrap_voc("spec2wav")

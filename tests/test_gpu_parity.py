@@ -195,10 +195,10 @@ def test_ragged_batch_is_per_item(math_mode):
 def test_batch_composition_invariance(monkeypatch):
     """Size-independent property at the BASELINE shape [B,128,1000]: an item's result does not depend on its batch.
 
-    Default tile selection: every contraction keeps one K-chain regardless of the grid -> bit-identical.
-    With the opt-in split-K conv kernel (DSVC_SPLITK=1: one tap per CTA of a 3-CTA cluster, partial tiles added
-    afterwards) a single clip and a 3-clip batch differ in fp32 summation order -> equal to rounding, and the
-    reduction order is fixed -> still deterministic."""
+    Within one tile class (same tile width, CTA pairs or not, no split-K) every contraction keeps one K-chain and one
+    summation order whatever the grid is -> bit-identical.  The launcher picks the tile width from the grid size
+    (waves x cost, tc_gemm.cuh), and the classes differ in the order in which the three partial products of the
+    error-compensated fp16 split are added -> across classes equal to fp32 rounding, and still deterministic."""
     cond, x0, noise = _inputs(3, 1000, 3, seed=5)
 
     def run(gd):
@@ -209,17 +209,23 @@ def test_batch_composition_invariance(monkeypatch):
         return full, one
 
     monkeypatch.delenv("DSVC_SPLITK", raising=False)
-    gd0, sd = _full_model("tc3f16")
-    full0, one0 = run(gd0)
-    assert torch.equal(full0[1:2], one0)
-    monkeypatch.setenv("DSVC_SPLITK", "1")
-    gd1, _ = _full_model("tc3f16")
+    for bn in ("64", "128"):                       # one tile class for both grids
+        monkeypatch.setenv("DSVC_TC_BN", bn)
+        gd0, sd = _full_model("tc3f16")
+        full0, one0 = run(gd0)
+        assert torch.equal(full0[1:2], one0), bn
+    monkeypatch.delenv("DSVC_TC_BN")
+    gd1, _ = _full_model("tc3f16")                 # the launcher's own choice: 128-wide tiles for 3 clips, 64-wide for 1
     full1, one1 = run(gd1)
-    assert torch.equal(full1, full0)               # the 3-clip grid is too large for split-K: same kernels
-    assert not torch.equal(one1, one0)             # the single clip did take the split-K kernel ...
-    assert (one1 - one0).abs().max().item() <= 2e-5 * one0.abs().max().item()     # ... same math, other order
-    one1b = gd1.sample(x0[1:2].to(DEV), cond[1:2].to(DEV), 3, None, noise[:, 1:2].contiguous().to(DEV)).cpu()
-    assert torch.equal(one1, one1b)
+    assert (full1[1:2] - one1).abs().max().item() <= 2e-5 * one1.abs().max().item()
+    monkeypatch.setenv("DSVC_SPLITK", "1")         # opt-in split-K conv of small grids: another order again
+    gd2, _ = _full_model("tc3f16")
+    full2, one2 = run(gd2)
+    assert torch.equal(full2, full1)               # the 3-clip grid is too large for split-K: same kernels
+    assert not torch.equal(one2, one1)             # the single clip did take the split-K kernel ...
+    assert (one2 - one1).abs().max().item() <= 2e-5 * one1.abs().max().item()     # ... same math, other order
+    one2b = gd2.sample(x0[1:2].to(DEV), cond[1:2].to(DEV), 3, None, noise[:, 1:2].contiguous().to(DEV)).cpu()
+    assert torch.equal(one2, one2b)
 
 
 def test_philox_stream_is_seeded():

@@ -70,8 +70,14 @@ def test_ddpm_chain_ragged_and_deterministic(monkeypatch):
     assert torch.equal(one, xf[1:2, :, :, :129])
 
 
-def test_vocoder_on_pair_kernels(monkeypatch):
-    """NSF-HiFiGAN ResBlock convs (k = 3 / 7 / 11 taps, dilations 1 / 3 / 5) through the same main loop."""
+@pytest.mark.parametrize("bn", [None, 128, 256])
+def test_vocoder_on_pair_kernels(monkeypatch, bn):
+    """NSF-HiFiGAN ResBlock convs (k = 3 / 7 / 11 taps, dilations 1 / 3 / 5) through the same main loop, in every tile
+    class (a 10 s clip takes the 128-wide class in its first stages, batches the 256-wide one)."""
+    if bn:
+        monkeypatch.setenv("DSVC_TC_BN", str(bn))
+    else:
+        monkeypatch.delenv("DSVC_TC_BN", raising=False)
     from diffsvc_b200.vocoders.nsf_hifigan import NsfHifiGAN
     from diffsvc_b200.hparams import hparams, DEFAULTS_44K
     hparams.clear(); hparams.update(DEFAULTS_44K)

@@ -2,7 +2,9 @@
 DSVC_LIB=diffsvc_b200/lib/libdsvc_tl.so python tools/dev_timeline.py [T]).  The library prints the stamps itself."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["DSVC_FUSED_LAYER"] = "2"
+PARTS = [int(x) for x in os.environ.get("DSVC_TL_PARTS", "0,1,2").split(",")]   # 2 = the fused layer kernel
+if 2 in PARTS:
+    os.environ["DSVC_FUSED_LAYER"] = "2"
 import torch
 import diffsvc_b200 as D
 from diffsvc_b200 import _lib
@@ -19,8 +21,9 @@ cond = (torch.randn(1, 256, T, generator=g) * 0.5).cuda(); x0 = torch.randn(1, 1
 gd.sample(x0, cond, 2, None, None, seed=1); torch.cuda.synchronize()
 h = dn.handle()
 print("== lib %s  T=%d" % (os.environ.get("DSVC_LIB", "product"), T), flush=True)
-for part in (0, 1, 2):
+for part in PARTS:
     _lib.check(lib.dsvc_diffnet_run_layer(h, 3, part, 4, _lib.current_stream())); torch.cuda.synchronize()
-os.environ["DSVC_FUSED_FENCE"] = "1"
-print("== fused, device-scope fence (DSVC_FUSED_FENCE=1)", flush=True)
-_lib.check(lib.dsvc_diffnet_run_layer(h, 3, 2, 4, _lib.current_stream())); torch.cuda.synchronize()
+if 2 in PARTS:
+    os.environ["DSVC_FUSED_FENCE"] = "1"
+    print("== fused, device-scope fence (DSVC_FUSED_FENCE=1)", flush=True)
+    _lib.check(lib.dsvc_diffnet_run_layer(h, 3, 2, 4, _lib.current_stream())); torch.cuda.synchronize()
