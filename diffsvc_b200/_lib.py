@@ -41,12 +41,26 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     tmp = out + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise DsvcError("nvcc failed:\n" + r.stdout + r.stderr)
+    # one nvcc per translation unit, in parallel (they share no device symbols), then one link
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = "%s.%s.o" % (tmp, src[:-3])
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        objs.append(obj)
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [(p.communicate()[0], p.returncode) for p in procs]
+    try:
+        if any(rc != 0 for _, rc in logs):
+            raise DsvcError("nvcc failed:\n" + "".join(l for l, _ in logs))
+        r = subprocess.run([nvcc, "-shared", "-o", tmp] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise DsvcError("nvcc link failed:\n" + r.stdout + r.stderr)
+    finally:
+        for o in objs:
+            if os.path.exists(o):
+                os.remove(o)
     os.replace(tmp, out)
     return out
 

@@ -44,6 +44,58 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// Packed ragged batch: the caller's [B][Cc][uT] tensor -> rows of the packed frame axis [Tp][Cc] (padding rows: zeros),
+// optional operand-plane copy.  Consecutive packed rows are consecutive frames of one item, so both sides coalesce.
+__global__ void pack_rows_kernel(const float* __restrict__ in, float* __restrict__ out, Plane pl, const int2* __restrict__ rowmap,
+                                 int Tp, int Cc, int uT) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
+  {
+    const int r = r0 + threadIdx.x;
+    const int2 m = r < Tp ? __ldg(rowmap + r) : make_int2(-1, 0);
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i;
+      tile[i][threadIdx.x] = (m.x >= 0 && c < Cc) ? in[((size_t)m.x * Cc + c) * uT + m.y] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < Tp && c < Cc) {
+      const float v = tile[threadIdx.x][i];
+      const size_t idx = (size_t)r * Cc + c;
+      if (out) out[idx] = v;
+      if (pl.f32) pl.f32[idx] = v;
+      if (pl.hi) {
+        __half h, l;
+        split_f16(v, h, l);
+        pl.hi[idx] = h;
+        pl.lo[idx] = l;
+      }
+    }
+  }
+}
+
+// the way back: rows of the packed axis [Tp][Cc] -> the live frames of the caller's [B][Cc][uT] tensor (frames at or
+// beyond an item's length keep what the caller passed in)
+__global__ void unpack_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const int2* __restrict__ rowmap,
+                                   int Tp, int Cc, int uT) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < Tp && c < Cc) ? in[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  const int r = r0 + threadIdx.x;
+  const int2 m = r < Tp ? __ldg(rowmap + r) : make_int2(-1, 0);
+  if (m.x < 0) return;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    if (c < Cc) out[((size_t)m.x * Cc + c) * uT + m.y] = tile[threadIdx.x][i];
+  }
+}
+
 // conditioning encoder (fs2.py:94-154 no_fs2 path): one block per (frame, item)
 __global__ void cond_encode_kernel(const float* __restrict__ hubert, const long long* __restrict__ mel2ph,
                                    const float* __restrict__ f0, const float* __restrict__ emb, int Th, int T, int H,
@@ -112,7 +164,10 @@ struct dsvc_diffnet {
   DevBuf c_recip, c_recipm1, c_coef1, c_coef2, c_logvar, c_acp;
   bool have_schedule = false;
   // workspace
-  int B = 0, Tmax = 0;
+  int B = 0, Tmax = 0;   // the layout the kernels run on: the caller's, or (1, Tp) for a packed batch
+  int uB = 0, uT = 0;    // the caller's batch size and Tmax (what x / cond / noise / eval outputs are laid out in)
+  DevBuf rowmap;         // packed batch: [Tp] (item, frame) per row, (-1, 0) = padding row
+  bool packed = false;
   bool prepared = false;
   DevBuf X, S, XS, hist, CP, cond_cl, lengths, state;
   PlaneBuf Y, Z, SP, R, XIN;
@@ -288,6 +343,7 @@ static EpiInProj::Params mk_inproj(const dsvc_diffnet* h, int tsel) {
   e.bias = h->b_in.as<float>(); e.dtab = h->dtab.as<float>(); e.st = h->state.as<StepState>(); e.lengths = h->lengths.as<int>();
   e.X = h->X.as<float>(); e.Y = h->Y.view(h->tc); e.Tmax = h->Tmax; e.C = h->cfg.residual_channels; e.L = h->cfg.residual_layers;
   e.tsel = tsel; e.wscale = h->tc ? h->h_in.inv_scale : 1.f;
+  e.rowmap = h->packed ? h->rowmap.as<int2>() : nullptr;
   return e;
 }
 static EpiGate::Params mk_gate(const dsvc_diffnet* h, int l) {
@@ -305,6 +361,7 @@ static EpiOutProj::Params mk_outproj(const dsvc_diffnet* h, int l, int tsel) {
   e.Y = ((h->pingpong && ((l + 1) & 1)) ? h->Y2 : h->Y).view(h->tc);   // the plane layer l+1's conv reads
   e.Tmax = h->Tmax; e.C = C; e.L = h->cfg.residual_layers; e.layer = l; e.tsel = tsel; e.fast = h->tc ? 1 : 0;
   e.wscale = h->tc ? h->h_out[l]->inv_scale : 1.f;
+  e.rowmap = h->packed ? h->rowmap.as<int2>() : nullptr;
   return e;
 }
 static EpiSkipProj::Params mk_skip(const dsvc_diffnet* h) {
@@ -321,6 +378,7 @@ static EpiHead::Params mk_head(const dsvc_diffnet* h, const HeadArgs& ha) {
   e.c_coef2 = h->c_coef2.as<float>(); e.c_logvar = h->c_logvar.as<float>();
   e.alphas_cumprod = h->c_acp.as<float>(); e.hist = h->hist.as<float>();
   e.wscale = h->tc ? h->h_head.inv_scale : 1.f;
+  e.rowmap = h->packed ? h->rowmap.as<int2>() : nullptr; e.uB = h->uB; e.uT = h->uT;
   return e;
 }
 
@@ -405,6 +463,9 @@ static int load_x(dsvc_diffnet* h, const float* spec, cudaStream_t s) {
   // [B][M][T] -> XS [B][T][M] (+ operand plane of input_projection)
   const int M = h->cfg.mel_bins;
   dim3 grid(ceil_div(h->Tmax, 32), ceil_div(M, 32), h->B), block(32, 8);
+  if (h->packed)
+    pack_rows_kernel<<<grid, block, 0, s>>>(spec, h->XS.as<float>(), h->XIN.view(h->tc), h->rowmap.as<int2>(), h->Tmax, M, h->uT);
+  else
   transpose_kernel<<<grid, block, 0, s>>>(spec, h->XS.as<float>(), h->XIN.view(h->tc), M, h->Tmax);
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
@@ -414,6 +475,9 @@ static int store_x(dsvc_diffnet* h, float* x, cudaStream_t s) {
   const int M = h->cfg.mel_bins;
   Plane none{nullptr, nullptr, nullptr};
   dim3 grid(ceil_div(M, 32), ceil_div(h->Tmax, 32), h->B), block(32, 8);
+  if (h->packed)
+    unpack_rows_kernel<<<dim3(ceil_div(h->Tmax, 32), ceil_div(M, 32)), block, 0, s>>>(h->XS.as<float>(), x, h->rowmap.as<int2>(), h->Tmax, M, h->uT);
+  else
   transpose_kernel<<<grid, block, 0, s>>>(h->XS.as<float>(), x, none, h->Tmax, M);
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
@@ -501,8 +565,36 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
       DSVC_REQUIRE(lengths[b] >= 0 && lengths[b] <= Tmax, "lengths[%d]=%d outside [0,%d]", b, lengths[b], Tmax);
       len[b] = lengths[b];
     }
-  const bool resized = (B != h->B || Tmax != h->Tmax);
-  h->B = B; h->Tmax = Tmax;
+  // Packed batch (tensor-core path, B > 1): the items lie back to back on ONE frame axis, G = max dilation rows of zero
+  // padding between them (the conv's zero padding of both neighbours: a tap never reaches further than G), the axis
+  // rounded up to whole 256-frame pair tiles.  No per-item tile rounding, no dead tile slots: 8 slices of 689 +- 25 %
+  // frames are 48 frame tiles = one wave of 256-wide tiles, where the per-item layout needs 50-52 tiles = two waves
+  // (measured 1716 -> see DESIGN.md 3.1e).  rowmap[row] = (item, frame); the caller-facing tensors (x, cond, noise,
+  // eval output) keep their [B][..][Tmax] layout and are gathered / scattered through it.  DSVC_PACK=0 disables.
+  const int user_B = B, user_T = Tmax;
+  bool pack = false;
+  {
+    const int cyc = h->cfg.dilation_cycle_length < L ? h->cfg.dilation_cycle_length : L;
+    const char* pe = getenv("DSVC_PACK");
+    pack = tc && B > 1 && cyc <= 7 && !(pe && atoi(pe) == 0);
+    if (pack) {
+      const int G = 1 << (cyc - 1);
+      std::vector<int2> rm;
+      for (int b = 0; b < B; ++b) {
+        for (int p = 0; p < len[b]; ++p) rm.push_back(make_int2(b, p));
+        if (b + 1 < B) rm.insert(rm.end(), (size_t)G, make_int2(-1, 0));
+      }
+      const int Tp = 2 * TC_BM * ceil_div((int)rm.size(), 2 * TC_BM);
+      rm.resize((size_t)Tp, make_int2(-1, 0));
+      DSVC_TRY(h->rowmap.reserve(rm.size() * sizeof(int2)));
+      DSVC_CUDA(cudaMemcpyAsync(h->rowmap.p, rm.data(), rm.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+      DSVC_CUDA(cudaStreamSynchronize(s));   // `rm` is a stack-owned staging buffer
+      B = 1; Tmax = Tp;
+      len.assign(1, Tp);
+    }
+  }
+  const bool resized = (B != h->B || Tmax != h->Tmax || pack != h->packed);
+  h->B = B; h->Tmax = Tmax; h->uB = user_B; h->uT = user_T; h->packed = pack;
   const size_t n = (size_t)B * Tmax;
   DSVC_TRY(h->X.reserve(n * C * 4));
   DSVC_TRY(h->S.reserve(n * C * 4));
@@ -561,6 +653,8 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
   {
     Plane none{nullptr, nullptr, nullptr};
     dim3 grid(ceil_div(Tmax, 32), ceil_div(H, 32), B), block(32, 8);
+    if (pack) pack_rows_kernel<<<grid, block, 0, s>>>(cond, h->cond_cl.as<float>(), none, h->rowmap.as<int2>(), Tmax, H, user_T);
+    else
     transpose_kernel<<<grid, block, 0, s>>>(cond, h->cond_cl.as<float>(), none, H, Tmax);
     DSVC_LAUNCH_CHECK();
     ConvGemmParams p = base_params(h->cond_cl.as<float>(), h->w_cond.as<float>(), B, Tmax, H, L * 2 * C, 1, 0);

@@ -62,6 +62,13 @@ __device__ __forceinline__ void plane_store4(const Plane& pl, size_t idx, const 
   }
 }
 
+// Packed ragged batches (diffnet.cu, dsvc_diffnet_prepare): the items of a batch lie back to back on ONE frame axis,
+// separated by max-dilation rows of zero padding; rowmap[row] = (item, frame) of the caller's [B][Tmax] layout, or
+// (-1, 0) for a padding row.  Null: the dense [B][Tmax] layout, padding = frames at or beyond the item's length.
+__device__ __forceinline__ bool row_live(const int2* rowmap, const int* lengths, int b, int p) {
+  return rowmap ? (__ldg(rowmap + p).x >= 0) : (p < lengths[b]);
+}
+
 // sigmoid(g) * tanh(f) from two ex2.approx and two rcp.approx:  1/(1+e^-g) * (1 - 2/(1+e^2f)).
 // Absolute error ~1e-7 on a value in (-1, 1) -- what matters for an operand of the next contraction;
 // used by the tensor-core path only (its own arithmetic error is ~1e-6), the FFMA path keeps expf/tanhf.
@@ -81,6 +88,7 @@ struct EpiInProj {
     const float* dtab;       // [Tn][L][C] diffusion-step shifts d_l(t)
     const StepState* st;
     const int* lengths;      // [B]
+    const int2* rowmap;      // packed batch: row -> (item, frame), null otherwise
     float* X;                // [B][Tmax][C] residual stream
     Plane Y;                 // (x + d_0) masked to the item's own length: what the dilated conv reads
     int Tmax, C, L;
@@ -102,7 +110,7 @@ struct EpiInProj {
                   fmaxf(a[2] * e.wscale + c.bias.z, 0.f), fmaxf(a[3] * e.wscale + c.bias.w, 0.f)};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
     *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
-    const bool live = p < e.lengths[b];
+    const bool live = row_live(e.rowmap, e.lengths, b, p);
     float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
     plane_store4(e.Y, idx, y);
   }
@@ -180,6 +188,7 @@ struct EpiOutProj {
     const float* dtab;       // [Tn][L][C]
     const StepState* st;
     const int* lengths;
+    const int2* rowmap;      // packed batch: row -> (item, frame), null otherwise
     float* X;                // [B][Tmax][C] in/out
     float* S;                // [B][Tmax][C] running skip sum
     Plane Y;                 // (x' + d_{l+1}) masked (not written by the last layer)
@@ -228,7 +237,7 @@ struct EpiOutProj {
       }
       *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
       if (e.layer + 1 < e.L) {
-        const bool live = p < e.lengths[b];
+        const bool live = row_live(e.rowmap, e.lengths, b, p);
         float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
         plane_store4(e.Y, idx, y);
       }
@@ -294,6 +303,8 @@ struct EpiHead {
     float* out;          // HEAD_EVAL: [B,1,M,Tmax]
     float* xs;           // sampler state x, channels-last [B][Tmax][M]
     Plane XIN;           // operand plane of input_projection for the next eval
+    const int2* rowmap;  // packed batch: row -> (item, frame) of the caller's layout (noise / Philox / HEAD_EVAL indexing)
+    int uB, uT;          // the caller's batch size and Tmax (== B, Tmax when rowmap is null)
     // DDPM
     const float* c_recip; const float* c_recipm1; const float* c_coef1; const float* c_coef2; const float* c_logvar;
     // PLMS
@@ -338,9 +349,15 @@ struct EpiHead {
                                                const EpiCol& c, const EpiPre& r) {
     const float eps[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.M + n;
+    int ub = b, up = p;                      // (item, frame) in the caller's [uB][..][uT] tensors
+    if (e.rowmap) {
+      const int2 r = __ldg(e.rowmap + p);
+      if (r.x < 0) return;                   // padding row of a packed batch: nothing of the caller's lives here
+      ub = r.x; up = r.y;
+    }
     if (e.mode == HEAD_EVAL) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) e.out[((size_t)b * e.M + n + i) * e.Tmax + p] = eps[i];
+      for (int i = 0; i < 4; ++i) e.out[((size_t)ub * e.M + n + i) * e.uT + up] = eps[i];
       return;
     }
     const float x[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
@@ -353,10 +370,10 @@ struct EpiHead {
       const float* noise = e.st->noise;
       if (noise) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nz[i] = __ldg(noise + (((size_t)e.st->step * e.B + b) * e.M + (n + i)) * e.Tmax + p);
+        for (int i = 0; i < 4; ++i) nz[i] = __ldg(noise + (((size_t)e.st->step * e.uB + ub) * e.M + (n + i)) * e.uT + up);
       } else {
         // library stream: one Philox4x32-10 call yields the 4 draws of this (step, item, frame, channel-quad)
-        const float4 q = philox_normal4(e.st->seed, 0x6e6f6973u, (((size_t)e.st->step * e.B + b) * (e.M >> 2) + (n >> 2)) * e.Tmax + p);
+        const float4 q = philox_normal4(e.st->seed, 0x6e6f6973u, (((size_t)e.st->step * e.uB + ub) * (e.M >> 2) + (n >> 2)) * e.uT + up);
         nz[0] = q.x; nz[1] = q.y; nz[2] = q.z; nz[3] = q.w;
       }
 #pragma unroll

@@ -302,10 +302,10 @@ int tc_pair_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B,
 // mode, the single-CTA kernel otherwise (1-pass "fast mode", the 256-wide tiles of large batches, odd widths).
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-              cudaStream_t s, TcTiles tt = TcTiles{}) {
+              cudaStream_t s, TcTiles tt = TcTiles{}, int bn_want = 0) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
   if (passes == 3 && tc_pair_enabled()) {
-    const int bn = tc_pick_bn(B, T, N, tt.live);
+    const int bn = bn_want > 0 ? bn_want : tc_pick_bn(B, T, N, tt.live);
     if (bn == 64 && N % 64 == 0) return tc_pair_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, s, tt);
     if (bn == 128 && N % 128 == 0) return tc_pair_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, s, tt);
     if (bn == 256 && N % 256 == 0) return tc_pair_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, s, tt);

@@ -177,9 +177,12 @@ def test_plms_chain_full(math_mode):
     assert err <= 1e-5, (math_mode, err, rng)
 
 
-@pytest.mark.parametrize("math_mode", ["fp32", "tc3f16"])
-def test_ragged_batch_is_per_item(math_mode):
-    """Each item of a ragged batch is computed as if alone: the oracle is a loop of B=1 calls."""
+@pytest.mark.parametrize("math_mode,pack", [("fp32", "1"), ("tc3f16", "1"), ("tc3f16", "0")])
+def test_ragged_batch_is_per_item(math_mode, pack, monkeypatch):
+    """Each item of a ragged batch is computed as if alone: the oracle is a loop of B=1 calls.
+    tc3f16 batches run PACKED by default (items back to back on one frame axis, max-dilation zero rows between them);
+    DSVC_PACK=0 keeps the per-item [B][Tmax] layout with its live-tile table."""
+    monkeypatch.setenv("DSVC_PACK", pack)
     steps, lens = 12, [150, 97, 33]
     T = max(lens)
     gd, sd = _full_model(math_mode)

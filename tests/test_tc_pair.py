@@ -100,10 +100,13 @@ def test_vocoder_on_pair_kernels(monkeypatch, bn):
     assert (outs[True] - outs[False]).abs().max().item() <= 5e-5
 
 
-def test_ragged_tile_table_follows_the_lengths(monkeypatch):
-    """Ragged batches run from a table of the frame tiles that hold a valid frame (dead slots exit).  One handle, one
-    (B, Tmax), three different length sets back to back -- the captured step graph is reused, only the table changes --
-    then full-length again (dense grid)."""
+@pytest.mark.parametrize("pack", ["0", "1"])
+def test_ragged_tile_table_follows_the_lengths(monkeypatch, pack):
+    """DSVC_PACK=0: ragged batches run from a table of the frame tiles that hold a valid frame (dead slots exit).  One
+    handle, one (B, Tmax), three different length sets back to back -- the captured step graph is reused, only the table
+    changes -- then full-length again (dense grid).  DSVC_PACK=1 (default): the same calls on the packed frame axis
+    (row map rebuilt per length set; the graph is re-captured when the packed length changes its 256-frame tile count)."""
+    monkeypatch.setenv("DSVC_PACK", pack)
     steps, B, T = 5, 3, 400
     cond, x0, noise = _inputs(B, T, steps, seed=77)
     gd, sd = _model(monkeypatch, True, K_step=steps)
