@@ -276,15 +276,16 @@ def cfg3_sliced_batch(gd, voc, dist, rank, world, flush, n_warm=1, n_timed=2):
     cond = ret0["decoder_inp"].transpose(1, 2).contiguous()
     x0 = torch.randn(len(mine), 1, MEL, T, device="cuda")
     f0hz_d = f0_hz.cuda()
-    busy, gather, total = [], [], []
+    busy, gather, total, samp = [], [], [], []
     for i in range(n_warm + n_timed):
         if dist is not None:
             dist.barrier()
         flush.fill_(float(i)); torch.cuda.synchronize()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
         with torch.no_grad():
             x = gd.sample(x0, cond, 1000, None, None, lengths=lens, seed=31 + i)
+            e[3].record()
             mel = gd.denorm_spec(x[:, 0].transpose(1, 2)).clamp(-6.0, 1.5)
             # the vocoder has no per-item boundary: vocode each slice alone (B = 1 semantics, as infer_tool.py:277 does)
             wavs = [voc.spec2wav_torch(mel[k:k + 1, :n], f0=f0hz_d[k:k + 1, :n], seed=8 * i + k) for k, n in enumerate(lens)]
@@ -295,7 +296,9 @@ def cfg3_sliced_batch(gd, voc, dist, rank, world, flush, n_warm=1, n_timed=2):
         e[2].record(); torch.cuda.synchronize()
         if i >= n_warm:
             busy.append(e[0].elapsed_time(e[1])); gather.append(e[1].elapsed_time(e[2])); total.append(e[0].elapsed_time(e[2]))
-    stats = torch.tensor([sum(busy) / n_timed, sum(gather) / n_timed, sum(total) / n_timed, float(sum(lens))], device="cuda", dtype=torch.float64)
+            samp.append(e[0].elapsed_time(e[3]))
+    stats = torch.tensor([sum(busy) / n_timed, sum(gather) / n_timed, sum(total) / n_timed, float(sum(lens)), sum(samp) / n_timed],
+                         device="cuda", dtype=torch.float64)
     if dist is not None:
         allst = [torch.empty_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
@@ -305,9 +308,13 @@ def cfg3_sliced_batch(gd, voc, dist, rank, world, flush, n_warm=1, n_timed=2):
     job_ms = float(allst[:, 2].max())
     audio = sum(lengths) * HOP / SR
     return {"workload": "BASELINE configs[3]: %d ragged slices (689 frames +- 25 %%, %.1f s audio in total), 1000-step DDPM + NSF-HiFiGAN, "
-                        "sharding.partition_slices -> ragged sub-batch per rank -> sharding.gather_waveforms" % (n_slices, audio),
+                        "sharding.partition_slices -> per-rank sub-batch, packed back to back on one frame axis (DESIGN.md 3.1e) -> "
+                        "sharding.gather_waveforms" % (n_slices, audio),
             "n_slices": n_slices, "audio_sec_per_s": audio / (job_ms / 1000.0), "job_ms": job_ms,
             "per_rank_busy_ms": [round(float(v), 2) for v in allst[:, 0]], "per_rank_frames": [int(v) for v in allst[:, 3]],
+            "per_rank_us_per_ddpm_step": [round(float(v), 1) for v in allst[:, 4]],          # sampler alone: ms per 1000 steps = us per step
+            "sampler_algorithmic_tflops_per_rank": [round(float(f) * FLOP_EVAL_PER_FRAME * 1000 / (float(v) * 1e-3) / 1e12, 1)
+                                                    for f, v in zip(allst[:, 3], allst[:, 4])],
             "gather_ms_max": float(allst[:, 1].max()), "imbalance": float(allst[:, 0].max() / allst[:, 0].mean()),
             "timed_passes": n_timed}
 
@@ -486,7 +493,7 @@ def main():
                 "per_rank_ms_per_step": [round(v, 3) for v in ranks_e2e],
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_hubert, h_mel2ph, h_f0, h_f0hz))),
                 "d2h_bytes_per_step": int(h_wav.numel() * 4), "api": "GaussianDiffusion.forward + NsfHifiGAN.spec2wav_torch"},
-        "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<EpiGate> (dilated conv + conditioner + gate, one layer)",
+        "roofline": {"bound": "tensor", "kernel": "tc_pair_kernel<EpiGate, 64> (dilated conv k3 + conditioner + gate of one layer; cta_group::2 CTA pairs)",
                      "achieved": conv_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": conv_tf / peak_burst,
                      "frac_executed": PASSES * conv_tf / peak_burst, "frac_ceiling_parity_mode": 1.0 / PASSES,
                      "audio_sec_per_s_ceiling_parity_mode": peak_burst * 1e12 / PASSES / (FLOP_EVAL_PER_FRAME * NS * SR / HOP),

@@ -31,6 +31,14 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def header_crc():
+    """CRC-32 of include/dsvc.h: compiled into the library (dsvc_abi()) and checked at load -- the struct layouts and
+    argtypes below are mirrored by hand, a library built from another header must not be called through them."""
+    import zlib
+    with open(os.path.join(_HERE, "..", "include", "dsvc.h"), "rb") as f:
+        return zlib.crc32(f.read()) & 0xFFFFFFFF
+
+
 def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile csrc/*.cu for sm_100a into diffsvc_b200/lib/libdsvc.so (nvcc cross-compiles without a GPU).
     `extra_flags` / `out`: developer variants (e.g. -DDSVC_TIMELINE) next to the product library, loaded via DSVC_LIB."""
@@ -45,7 +53,8 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     objs, procs = [], []
     for src in SOURCES:
         obj = "%s.%s.o" % (tmp, src[:-3])
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-DDSVC_ABI_HASH=0x%08xu" % header_crc()] + list(extra_flags) \
+            + ["-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             print(" ".join(cmd))
         objs.append(obj)
@@ -124,6 +133,7 @@ class PeWeights(C.Structure):
 _VP = C.c_void_p
 SYMBOLS = [
     ("dsvc_version", C.c_char_p, []),
+    ("dsvc_abi", C.c_uint32, []),
     ("dsvc_last_error", C.c_char_p, []),
     ("dsvc_device_count", C.c_int, []),
     ("dsvc_launch_count", C.c_uint64, []),
@@ -172,6 +182,10 @@ def load():
         fn = getattr(lib, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    abi = lib.dsvc_abi()
+    if abi != 0 and abi != header_crc():
+        raise DsvcError("%s was built from another include/dsvc.h (abi %08x, header %08x): rebuild it "
+                        "(python -c 'import __graft_entry__ as g; g.build()')" % (path, abi, header_crc()))
     _lib = lib
     return lib
 

@@ -36,7 +36,8 @@ class CondEncoder(nn.Module):
 
     def forward(self, hubert, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None, energy=None,
                 skip_decoder=True, spk_embed_dur_id=None, spk_embed_f0_id=None, infer=False, **kwargs):
-        if not hparams.get("no_fs2", True) or hparams.get("use_spk_embed") or hparams.get("use_spk_id") \
+        # a missing `no_fs2` means "encoder enabled" in the reference (fs2.py:98): not this stand-alone module's job
+        if not hparams.get("no_fs2", False) or hparams.get("use_spk_embed") or hparams.get("use_spk_id") \
                 or hparams.get("use_energy_embed") or hparams.get("pitch_norm", "log") != "log":
             raise NotImplementedError("stand-alone CondEncoder covers the config_nsf.yaml conditioning only; "
                                       "run inside the reference tree to use its FastSpeech2")

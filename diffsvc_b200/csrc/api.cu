@@ -44,6 +44,10 @@ int require_device() {
 extern "C" {
 
 const char* dsvc_version(void) { return "diffsvc-b200 0.1.0 (sm_100a)"; }
+#ifndef DSVC_ABI_HASH
+#define DSVC_ABI_HASH 0u   /* built without the in-tree build script: the binding then skips the check */
+#endif
+uint32_t dsvc_abi(void) { return (uint32_t)DSVC_ABI_HASH; }
 const char* dsvc_last_error(void) { return dsvc::g_err; }
 
 int dsvc_device_count(void) {

@@ -6,6 +6,7 @@
 #include "tc_pair.cuh"
 #include "tc_splitk.cuh"
 #include "tc_layer.cuh"
+#include "tc_step.cuh"
 
 #include <cmath>
 #include <memory>
@@ -177,6 +178,9 @@ struct dsvc_diffnet {
   TcMaps maps;           // TMA descriptors of the tcgen05 path (rebuilt in prepare)
   DevBuf tile_tab;       // ragged batches: (item, first frame) of every frame tile with a valid frame, dead slots (0,-1) behind
   int tile_slots = 0, tile_live = 0;   // 0 slots: dense grid (all items full length)
+  DevBuf step_flags;     // step kernel (tc_step.cuh): [2][n_ft][32] dependency counters + the launch sequence word
+  int step_bn = 0;       // slot width of the step kernel for this (B, Tmax), 0: per-layer kernels
+  int step_pairs = 0;    // its grid: resident CTA pairs (each owns ceil(slots / pairs) slots)
   DevBuf sk_slab;        // split-K partial tiles [B][m_tiles][n_tiles][3][128][128] fp32 (tc_splitk.cuh)
   int num_sms = 148;
   // CUDA graphs of one sampler step
@@ -429,10 +433,89 @@ static bool fused_layers(const dsvc_diffnet* h) {
   return tc_layer_env() >= 2 || (long long)ceil_div(h->Tmax, TC_BM) * h->B <= h->fused_usable;
 }
 
+// The whole evaluation as ONE launch (tc_step.cuh): phase table, tensor maps and epilogue parameter blocks of the 2L+3
+// contractions in one kernel parameter.
+static int enqueue_eval_step(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
+  const int bn = h->step_bn;
+  static thread_local StepPlan plan;            // ~22 KB: not on the stack
+  auto put = [&](int at, const TcGemmMaps& g, bool a_side) {
+    if (a_side) { plan.maps[at] = g.a_hi; plan.maps[at + 1] = g.a_lo; }
+    else if (bn == 64) { plan.maps[at] = g.b32_hi; plan.maps[at + 1] = g.b32_lo; }
+    else { plan.maps[at] = g.b64_hi; plan.maps[at + 1] = g.b64_lo; }
+  };
+  put(STEP_MAP_XIN, h->maps.in, true);  put(STEP_MAP_IN, h->maps.in, false);
+  put(STEP_MAP_SP, h->maps.skip, true); put(STEP_MAP_SKIP, h->maps.skip, false);
+  put(STEP_MAP_R, h->maps.head, true);  put(STEP_MAP_HEAD, h->maps.head, false);
+  put(STEP_MAP_Y, h->maps.dil[0], true); put(STEP_MAP_Z, h->maps.out[0], true);
+  plan.maps[4] = plan.maps[2]; plan.maps[5] = plan.maps[3];      // (slots of a second conv-input plane: unused)
+  for (int l = 0; l < L; ++l) {
+    put(STEP_MAP_LAYER0 + 4 * l, h->maps.dil[l], false);
+    put(STEP_MAP_LAYER0 + 4 * l + 2, h->maps.out[l], false);
+  }
+  plan.n_maps = STEP_MAP_LAYER0 + 4 * L;
+  plan.in = mk_inproj(h, ha.tsel);
+  plan.skip = mk_skip(h);
+  plan.head = mk_head(h, ha);
+  int np = 0, done = 0;
+  auto phase = [&](int kind, int K, int taps, int dil, int N, int n_tiles, int a_map, int b_map, int epi) {
+    StepPhase& p = plan.phase[np++];
+    p.kind = kind; p.K = K; p.taps = taps; p.dil = dil; p.N = N; p.n_tiles = n_tiles; p.a_map = a_map; p.b_map = b_map;
+    p.expect = STEP_SIGNALS * done; p.epi = epi;
+    done += n_tiles;
+  };
+  phase(STEP_IN, M, 1, 0, C, C / bn, STEP_MAP_XIN, STEP_MAP_IN, 0);
+  for (int l = 0; l < L; ++l) {
+    plan.gate[l] = mk_gate(h, l);
+    plan.out[l] = mk_outproj(h, l, ha.tsel);
+    phase(STEP_GATE, C, 3, 1 << (l % h->cfg.dilation_cycle_length), 2 * C, 2 * C / bn, STEP_MAP_Y, STEP_MAP_LAYER0 + 4 * l, l);
+    phase(STEP_OUT, C, 1, 0, 2 * C, 2 * C / bn, STEP_MAP_Z, STEP_MAP_LAYER0 + 4 * l + 2, l);
+  }
+  phase(STEP_SKIP, C, 1, 0, C, C / bn, STEP_MAP_SP, STEP_MAP_SKIP, 0);
+  phase(STEP_HEAD, C, 1, 0, M, M / bn, STEP_MAP_R, STEP_MAP_HEAD, 0);
+  plan.n_phases = np;
+  plan.final = STEP_SIGNALS * done;
+  plan.n_ft = ceil_div(h->Tmax, 2 * TC_BM);
+  plan.n_slots = 2 * C / bn;
+  plan.T = h->Tmax;
+  plan.flags = h->step_flags.as<unsigned>();
+  plan.seq = plan.flags + (size_t)2 * plan.n_ft * 32;
+  return bn == 64 ? tc_step_launch<64>(plan, h->step_pairs, s) : tc_step_launch<128>(plan, h->step_pairs, s);
+}
+
+// Slot width of the step kernel for the prepared shape, 0 when it does not apply: the tensor-core 3-pass path on CTA
+// pairs, one item on the frame axis (a single clip or a packed batch), every channel count a multiple of the width, and
+// all (frame tile, channel tile) pairs resident at once.
+static int step_pick_bn(dsvc_diffnet* h) {
+  const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
+  if (!(h->tc && h->passes == 3 && tc_pair_enabled() && tc_step_enabled())) return 0;
+  if (h->B != 1 || h->tile_slots > 0 || L > STEP_MAXL || h->pingpong) return 0;
+  if (tc_forced_bn() > 0) return 0;               // a forced tile width means the per-layer kernels (tests of the tile classes)
+  const int n_ft = ceil_div(h->Tmax, 2 * TC_BM);
+  static int cap64 = -1, cap128 = -1;
+  if (cap64 < 0) { int a = 0, b = 0; if (tc_step_max_pairs<64>(&a) != DSVC_OK || tc_step_max_pairs<128>(&b) != DSVC_OK) return 0; cap64 = a; cap128 = b; }
+  // one clip (latency): 64-wide slots, one per pair.  Batches (throughput): 128-wide slots, two or more per pair --
+  // the pair works on one slot while the other's hand-over is in flight.
+  const char* sb = getenv("DSVC_STEP_BN");
+  const int want = sb ? atoi(sb) : 0;
+  if (want != 128 && M % 64 == 0 && C % 64 == 0 && cap64 > 0 && (n_ft * (2 * C / 64) <= cap64 || want == 64)) {
+    const int S = n_ft * (2 * C / 64), R = ceil_div(S, cap64);
+    h->step_pairs = ceil_div(S, R);
+    return 64;
+  }
+  if (M % 128 == 0 && C % 128 == 0 && cap128 > 0) {
+    const int S = n_ft * (2 * C / 128), R = ceil_div(S, cap128);
+    h->step_pairs = ceil_div(S, R);
+    return 128;
+  }
+  return 0;
+}
+
 // one denoiser evaluation: enqueue all kernels on `s`
 static int enqueue_eval(dsvc_diffnet* h, const HeadArgs& ha, cudaStream_t s) {
   const int M = h->cfg.mel_bins, C = h->cfg.residual_channels, L = h->cfg.residual_layers;
   const int B = h->B, T = h->Tmax;
+  if (h->step_bn > 0) return enqueue_eval_step(h, ha, s);
   {  // K0 input_projection + ReLU
     const EpiInProj::Params e = mk_inproj(h, ha.tsel);
     if (h->tc) DSVC_TRY(tc_launch<EpiInProj>(h->maps.in, e, B, T, M, C, 1, 0, h->passes, s, tiles_of(h)));
@@ -649,6 +732,16 @@ int dsvc_diffnet_prepare(dsvc_diffnet_t* h, int32_t B, int32_t Tmax, const int32
     h->g_ddpm_valid = h->g_plms_valid = false;
     if (tc) DSVC_TRY(tc_build_maps(h));
   }
+  {
+    const int bn = step_pick_bn(h);
+    if (bn != h->step_bn) h->g_ddpm_valid = h->g_plms_valid = false;
+    h->step_bn = bn;
+    if (bn > 0) {
+      const size_t fb = ((size_t)2 * ceil_div(Tmax, 2 * TC_BM) * 32 + 32) * sizeof(unsigned);
+      DSVC_TRY(h->step_flags.reserve(fb));
+      DSVC_CUDA(cudaMemsetAsync(h->step_flags.p, 0, fb, s));      // both counter sets and the sequence word start at 0
+    }
+  }
   // cond [B][H][T] -> channels-last, then all L conditioner projections in one GEMM
   {
     Plane none{nullptr, nullptr, nullptr};
@@ -696,7 +789,53 @@ int dsvc_cond_encode(const float* hubert, const int64_t* mel2ph, const float* f0
 int dsvc_diffnet_run_layer(dsvc_diffnet_t* h, int32_t layer, int32_t part, int32_t iters, void* stream) {
   DSVC_REQUIRE(h, "dsvc_diffnet_run_layer: null handle");
   if (!h->prepared) { set_error("dsvc_diffnet_run_layer: call dsvc_diffnet_prepare first"); return DSVC_ESTATE; }
-  DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && part >= 0 && part <= 2 && iters >= 0, "bad layer/part/iters");
+  DSVC_REQUIRE(layer >= 0 && layer < h->cfg.residual_layers && part >= 0 && part <= 3 && iters >= 0, "bad layer/part/iters");
+  if (part == 3) {
+    // developer probe: `iters` whole evaluations through the step kernel; a -DDSVC_TIMELINE build prints its phase stamps
+    if (h->step_bn == 0) { set_error("dsvc_diffnet_run_layer: part 3 needs the step kernel (tc_step.cuh) for this shape"); return DSVC_ESTATE; }
+    cudaStream_t s3 = (cudaStream_t)stream;
+    set_state_kernel<<<1, 1, 0, s3>>>(h->state.as<StepState>(), 500, 1, 1ull, nullptr);
+    DSVC_LAUNCH_CHECK();
+    HeadArgs ha3; ha3.mode = HEAD_DDPM;
+    for (int i = 0; i < iters; ++i) DSVC_TRY(enqueue_eval(h, ha3, s3));
+#ifdef DSVC_TIMELINE
+    {
+      static long long tl[160][2 * STEP_MAXL + 3][10];
+      DSVC_CUDA(cudaStreamSynchronize(s3));
+      DSVC_CUDA(cudaMemcpyFromSymbol(tl, g_step_tl, sizeof(tl)));
+      const int np = 2 * h->cfg.residual_layers + 3;
+      const int nct = 2 * h->step_pairs;
+      printf("step kernel timeline (last launch), cycles.  per phase of CTA c: start->deps | deps->first operands | first->MMAs issued | "
+             "issued->acc ready | acc->staged | staged->epi done | epi->signalled | phase total || start, ns after CTA 0's\n");
+      const int show[6] = {0, 1, 2, nct / 2, nct - 2, nct - 1};
+      for (int k = 0; k < 6; ++k) {
+        const int c = show[k];
+        if (c < 0 || c >= 160) continue;
+        for (int ph = 9; ph < 15 && ph < np; ++ph) {
+          const long long* t = tl[c][ph];
+          const long long first = (c & 1) ? tl[c - 1][ph][2] : t[2], issued = (c & 1) ? tl[c - 1][ph][3] : t[3];
+          printf("  cta %3d ph %2d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld || %7lld\n", c, ph, t[1] - t[0], (c & 1) ? -1 : first - t[1],
+                 (c & 1) ? -1 : issued - first, (c & 1) ? -1 : t[4] - issued, t[5] - t[4], t[6] - t[5], t[7] - t[6],
+                 tl[c][ph + 1][0] - t[0], t[8] - tl[0][ph][8]);
+        }
+      }
+      // averages over the conv (odd) and out-projection (even >= 2) phases of the even CTAs
+      for (int par = 0; par < 2; ++par) {
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int n = 0;
+        for (int c = 0; c < nct && c < 160; c += 2)
+          for (int ph = 1 + par; ph < np - 2; ph += 2) {
+            const long long* t = tl[c][ph];
+            a[0] += t[1] - t[0]; a[1] += t[2] - t[1]; a[2] += t[3] - t[2]; a[3] += t[4] - t[3]; a[4] += t[5] - t[4]; a[5] += t[6] - t[5];
+            a[6] += t[7] - t[6]; a[7] += tl[c][ph + 1][0] - t[0]; ++n;
+          }
+        printf("  mean %s: deps %.0f | first operands %.0f | MMA issue %.0f | acc ready %.0f | staged %.0f | epi %.0f | signal %.0f | total %.0f\n",
+               par ? "out-proj" : "conv    ", a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n, a[6] / n, a[7] / n);
+      }
+      fflush(stdout);
+    }
+#endif
+    return DSVC_OK;
+  }
   if (part == 2 && !fused_layers(h)) {
     set_error("dsvc_diffnet_run_layer: part 2 (fused layer kernel) needs DSVC_FUSED_LAYER and a tensor-core handle whose "
               "2C/64 channel tiles form a schedulable cluster");

@@ -36,7 +36,22 @@ struct Plane {
 };
 
 struct EpiCol { float4 bias; float4 d; };
-struct EpiPre { float4 a; float4 b; };
+struct EpiPre { float4 a; float4 b; int2 row; };   // row: raw row_of() lookup (see row_live)
+
+// Row validity of internal row (b, p), in two halves so that the LOAD can be batched with the other per-row inputs (one
+// round of independent loads, issued while the MMAs run) and nothing waits on it before apply():
+//   row_of()   the raw lookup: the row map entry (item, frame) of a packed batch, else (length of item b, p)
+//   row_live() padding test on that raw value: item < 0 (packed) or p >= length
+// A lookup inside apply() -- between the stores of consecutive rows -- serialises one L2 round trip per row; a lookup
+// whose RESULT is consumed inside pre() serialises the pre-loads of the MMA issuer warp, which enters the epilogue last
+// (measured: +1 us per out-projection kernel).
+__device__ __forceinline__ int2 row_of(const int2* rowmap, const int* lengths, int b, int p) {
+  if (rowmap) return __ldg(rowmap + p);
+  return make_int2(__ldg(lengths + b), p);
+}
+__device__ __forceinline__ bool row_live(const int2* rowmap, const int2& row) {
+  return rowmap ? row.x >= 0 : row.y < row.x;
+}
 
 __device__ __forceinline__ void l2_prefetch_line(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -65,9 +80,6 @@ __device__ __forceinline__ void plane_store4(const Plane& pl, size_t idx, const 
 // Packed ragged batches (diffnet.cu, dsvc_diffnet_prepare): the items of a batch lie back to back on ONE frame axis,
 // separated by max-dilation rows of zero padding; rowmap[row] = (item, frame) of the caller's [B][Tmax] layout, or
 // (-1, 0) for a padding row.  Null: the dense [B][Tmax] layout, padding = frames at or beyond the item's length.
-__device__ __forceinline__ bool row_live(const int2* rowmap, const int* lengths, int b, int p) {
-  return rowmap ? (__ldg(rowmap + p).x >= 0) : (p < lengths[b]);
-}
 
 // sigmoid(g) * tanh(f) from two ex2.approx and two rcp.approx:  1/(1+e^-g) * (1 - 2/(1+e^2f)).
 // Absolute error ~1e-7 on a value in (-1, 1) -- what matters for an operand of the next contraction;
@@ -103,14 +115,18 @@ struct EpiInProj {
     return c;
   }
   __device__ static __forceinline__ void l2_prefetch(const Params&, int, int, int) {}
-  __device__ static __forceinline__ EpiPre pre(const Params&, int, int, int) { return EpiPre{}; }
+  __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int) {
+    EpiPre r{};
+    r.row = row_of(e.rowmap, e.lengths, b, p);
+    return r;
+  }
   __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
-                                               const EpiCol& c, const EpiPre&) {
+                                               const EpiCol& c, const EpiPre& r) {
     float x[4] = {fmaxf(a[0] * e.wscale + c.bias.x, 0.f), fmaxf(a[1] * e.wscale + c.bias.y, 0.f),
                   fmaxf(a[2] * e.wscale + c.bias.z, 0.f), fmaxf(a[3] * e.wscale + c.bias.w, 0.f)};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.C + n;
     *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
-    const bool live = row_live(e.rowmap, e.lengths, b, p);
+    const bool live = row_live(e.rowmap, r.row);
     float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
     plane_store4(e.Y, idx, y);
   }
@@ -220,6 +236,7 @@ struct EpiOutProj {
     EpiPre r{};
     const float* s = src(e, b, p, n);
     if (s) r.a = *reinterpret_cast<const float4*>(s);
+    if (n < e.C && e.layer + 1 < e.L) r.row = row_of(e.rowmap, e.lengths, b, p);
     return r;
   }
   __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4],
@@ -237,7 +254,7 @@ struct EpiOutProj {
       }
       *reinterpret_cast<float4*>(e.X + idx) = make_float4(x[0], x[1], x[2], x[3]);
       if (e.layer + 1 < e.L) {
-        const bool live = row_live(e.rowmap, e.lengths, b, p);
+        const bool live = row_live(e.rowmap, r.row);
         float y[4] = {live ? x[0] + c.d.x : 0.f, live ? x[1] + c.d.y : 0.f, live ? x[2] + c.d.z : 0.f, live ? x[3] + c.d.w : 0.f};
         plane_store4(e.Y, idx, y);
       }
@@ -342,6 +359,7 @@ struct EpiHead {
   __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int n) {
     EpiPre r{};
     if (e.mode != HEAD_EVAL) r.a = *reinterpret_cast<const float4*>(e.xs + ((size_t)b * e.Tmax + p) * e.M + n);
+    r.row = e.rowmap ? __ldg(e.rowmap + p) : make_int2(b, p);
     return r;
   }
 
@@ -349,12 +367,8 @@ struct EpiHead {
                                                const EpiCol& c, const EpiPre& r) {
     const float eps[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     const size_t idx = ((size_t)b * e.Tmax + p) * e.M + n;
-    int ub = b, up = p;                      // (item, frame) in the caller's [uB][..][uT] tensors
-    if (e.rowmap) {
-      const int2 r = __ldg(e.rowmap + p);
-      if (r.x < 0) return;                   // padding row of a packed batch: nothing of the caller's lives here
-      ub = r.x; up = r.y;
-    }
+    const int ub = r.row.x, up = r.row.y;    // (item, frame) in the caller's [uB][..][uT] tensors
+    if (ub < 0) return;                      // padding row of a packed batch: nothing of the caller's lives here
     if (e.mode == HEAD_EVAL) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) e.out[((size_t)ub * e.M + n + i) * e.uT + up] = eps[i];
@@ -493,23 +507,25 @@ struct EpiVoc {
     const float* res;    // [B][Lout][Cout] fp32 or null
     float* out;          // [B][Lout][Cout] fp32 or null
     Plane act;           // hi/lo planes [B][Lout][Cout] or {null}
-    int Lout, Cout;
+    int Lout, Cout;      // Cout: the real channel count (a narrow conv's weight rows are zero-padded to the 64-wide tile)
     int accumulate;      // out = out + v
     float div, slope, wscale;
   };
   __device__ static __forceinline__ EpiCol col(const Params& e, int n) {
     EpiCol c;
-    c.bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    c.bias = n < e.Cout ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     c.d = make_float4(0.f, 0.f, 0.f, 0.f);
     return c;
   }
   __device__ static __forceinline__ void l2_prefetch(const Params& e, int b, int p, int n) {
+    if (n >= e.Cout) return;
     const size_t idx = ((size_t)b * e.Lout + p) * e.Cout + n;
     if (e.res) l2_prefetch_line(e.res + idx);
     if (e.accumulate) l2_prefetch_line(e.out + idx);
   }
   __device__ static __forceinline__ EpiPre pre(const Params& e, int b, int p, int n) {
     EpiPre r{};
+    if (n >= e.Cout) return r;
     const size_t idx = ((size_t)b * e.Lout + p) * e.Cout + n;
     if (e.res) r.a = *reinterpret_cast<const float4*>(e.res + idx);
     if (e.accumulate) r.b = *reinterpret_cast<const float4*>(e.out + idx);
@@ -517,6 +533,7 @@ struct EpiVoc {
   }
   __device__ static __forceinline__ void apply(const Params& e, int b, int p, int n, const float (&a)[4], const EpiCol& c,
                                                const EpiPre& r) {
+    if (n >= e.Cout) return;                 // padding columns of a narrow conv's 64-wide tile
     float v[4] = {a[0] * e.wscale + c.bias.x, a[1] * e.wscale + c.bias.y, a[2] * e.wscale + c.bias.z, a[3] * e.wscale + c.bias.w};
     if (e.res) { v[0] = add_rn(v[0], r.a.x); v[1] = add_rn(v[1], r.a.y); v[2] = add_rn(v[2], r.a.z); v[3] = add_rn(v[3], r.a.w); }
     if (e.accumulate) { v[0] = add_rn(r.b.x, v[0]); v[1] = add_rn(r.b.y, v[1]); v[2] = add_rn(r.b.z, v[2]); v[3] = add_rn(r.b.w, v[3]); }

@@ -250,6 +250,8 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
                                             , long long tl0, int tl_off = 0
 #endif
                                             , int pair_h = 0   // tc_pair.cuh accumulator layout: channel j adds column j + (j < h ? 3h : h)
+                                            , uint32_t acc_free_bar = 0   // tc_step.cuh: shared::cluster address of the barrier that hands the
+                                                                          // accumulator back to the MMA issuer (one arrive per warp), 0: none
 ) {
 #ifndef DSVC_TIMELINE
     constexpr int tl_off = 0;
@@ -330,16 +332,26 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW + c0);
         tmem_ld_cols<LW>(taddr, v);
         if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
-          float v2[LW];
           const uint32_t partner = pair_h == 0 ? (uint32_t)BN : (uint32_t)((cg * CW + c0) < pair_h ? 3 * pair_h : pair_h);
-          tmem_ld_cols<LW>(taddr + partner, v2);
+          constexpr int PW = LW > 16 ? 16 : LW;  // in pieces of <= 16 columns: 48, not 64, accumulator registers live
 #pragma unroll
-          for (int j = 0; j < LW; ++j) v[j] += v2[j];
+          for (int c1 = 0; c1 < LW; c1 += PW) {
+            float v2[PW];
+            tmem_ld_cols<PW>(taddr + partner + (uint32_t)c1, v2);
+#pragma unroll
+            for (int j = 0; j < PW; ++j) v[c1 + j] += v2[j];
+          }
         }
 #pragma unroll
         for (int j = 0; j < LW / 4; ++j)
           *reinterpret_cast<float4*>(slab + lane * STG_LD + cg * CW + c0 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
+    }
+    if (acc_free_bar != 0) {
+      // persistent kernels: this warp's tcgen05.ld's have completed (tcgen05.wait::ld above): the accumulator buffer may be
+      // overwritten by the next tile's MMAs while the functor below still runs
+      tc_fence_before();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_free_bar) : "memory");
     }
     asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the 4 warps of this quarter
     if (warp == 4) TL_MARK(5 + tl_off);    // staged to smem
@@ -349,15 +361,22 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       const int ncol = col_of(h);
       const bool col_ok = Epi::kPair ? true : (ncol < N);
       const int ch = lc + h * LPR;
-      EpiPre pre[NIT];
+      // row inputs in batches of <= 4 rows when they were not loaded early (wide tiles): 8 rows x (2 float4 + row id)
+      // would hold 80 registers across the whole functor loop
+      constexpr int RCH = kHoist ? NIT : (NIT > 4 ? 4 : NIT);
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
+      for (int i0 = 0; i0 < NIT; i0 += RCH) {
+      EpiPre pre[RCH];
+#pragma unroll
+      for (int ii = 0; ii < RCH; ++ii) {
+        const int i = i0 + ii;
         const int p = m0 + row0 + i * RPI + rsub;
-        if constexpr (kHoist) pre[i] = hpre[h * NIT + i];
-        else if (p < T && col_ok) pre[i] = Epi::pre(ep, b, p, ncol);
+        if constexpr (kHoist) pre[ii] = hpre[h * NIT + i];
+        else if (p < T && col_ok) pre[ii] = Epi::pre(ep, b, p, ncol);
       }
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
+      for (int ii = 0; ii < RCH; ++ii) {
+        const int i = i0 + ii;
         const int r = i * RPI + rsub;
         const int p = m0 + row0 + r;
         if constexpr (Epi::kPair) {
@@ -366,17 +385,19 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
           if (p < T) {
             const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
             const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
-            Epi::apply_pair(ep, b, p, ncol, gg, ff, cc[h], pre[i]);
+            Epi::apply_pair(ep, b, p, ncol, gg, ff, cc[h], pre[ii]);
           }
         } else {
           const float4 xv = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * ch);
           if (p < T && col_ok) {
             const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
-            Epi::apply(ep, b, p, ncol, vv, cc[h], pre[i]);
+            Epi::apply(ep, b, p, ncol, vv, cc[h], pre[ii]);
           }
         }
       }
+      }
     }
+    if (acc_free_bar != 0) asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");   // the slab is staged again by the next tile
 }
 
 // ---- the kernel -----------------------------------------------------------------------------

@@ -105,6 +105,10 @@ class GaussianDiffusion(nn.Module):
     def sample(self, x, cond, t, pndm_speedup=None, noise=None, lengths=None, seed=None):
         """The loop of diffusion.py:269-278 on the device.  x [B,1,M,T] (consumed), cond [B,H,T].
         noise: optional [t,B,1,M,T] injected N(0,1) draws (DDPM), else the library's Philox stream."""
+        with torch.cuda.device(cond.device):      # the handle's kernels launch on the current device: the tensors' own
+            return self._sample(x, cond, t, pndm_speedup, noise, lengths, seed)
+
+    def _sample(self, x, cond, t, pndm_speedup, noise, lengths, seed):
         h = self.denoise_fn.prepare(cond, lengths)
         self._sync_schedule(h)
         x = x.detach().to(torch.float32).contiguous().clone()

@@ -166,7 +166,8 @@ class DiffNet(nn.Module):
             lens = (C.c_int32 * B)(*[int(v) for v in lengths])
         key = (cond.data_ptr(), cond._version, tuple(cond.shape), None if lengths is None else tuple(int(v) for v in lengths))
         if key != self._cond_key:
-            _lib.check(_lib.load().dsvc_diffnet_prepare(h, B, T, lens, _lib.dptr(cond), _lib.current_stream()))
+            with torch.cuda.device(cond.device):     # the handle's kernels launch on the current device: the tensors' own
+                _lib.check(_lib.load().dsvc_diffnet_prepare(h, B, T, lens, _lib.dptr(cond), _lib.current_stream()))
             self._cond_key = key
             self._keep = cond
         return h
@@ -180,5 +181,6 @@ class DiffNet(nn.Module):
             raise ValueError("all batch items must share the diffusion step (the reference's sampler does)")
         spec = spec.detach().to(torch.float32).contiguous()
         out = torch.empty_like(spec)
-        _lib.check(_lib.load().dsvc_diffnet_eval(h, _lib.dptr(spec), t, _lib.dptr(out), _lib.current_stream()))
+        with torch.cuda.device(spec.device):
+            _lib.check(_lib.load().dsvc_diffnet_eval(h, _lib.dptr(spec), t, _lib.dptr(out), _lib.current_stream()))
         return out

@@ -42,6 +42,9 @@ extern "C" {
 #define DSVC_MATH_TC1F16   2  /* tcgen05, single fp16 pass: "fast mode", NOT within the parity gate */
 
 const char* dsvc_version(void);
+/* CRC-32 of this header as the library was built against it.  Bindings that mirror the structs below by hand (ctypes)
+ * compare it with the CRC-32 of the header they were written for and refuse a library built from another one. */
+uint32_t dsvc_abi(void);
 const char* dsvc_last_error(void);
 /* number of sm_100 devices visible (0 on a CPU-only box); never fails */
 int dsvc_device_count(void);

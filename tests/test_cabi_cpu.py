@@ -20,6 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert b"sm_100a" in lib.dsvc_version()
+    assert lib.dsvc_abi() == _lib.header_crc()          # the library was built from THIS include/dsvc.h
 
 
 def test_struct_layouts_match_header():
