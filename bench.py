@@ -230,7 +230,7 @@ def run_reference(args, rank):
                                             "that sample), DDPM part extrapolated linearly to the clip; %s, torch CPU fp32, %d threads "
                                             "(autotuned of %d cpus)" % (n, args.ddpm_steps, T, _kind_text(ref.kind), threads, os.cpu_count() or 1)},
                  "e2e": {"value": val, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _kind_text(kind):
@@ -376,7 +376,21 @@ def profile_traffic(B, T):
         return None, None
 
 
+def emit(line):
+    """The ONE JSON line, on the real stdout (fd saved in main() before everything else was pointed at stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner at communicator creation,
+    # the reference's progress output) are sent to stderr for the whole run, at the file-descriptor level
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -535,7 +549,7 @@ def main():
                                           "extrapolated linearly; %s, torch CPU fp32, %d threads"
                                           % (args.ref_ddpm_sample, NS, td, tv, T, _kind_text(ref.kind), threads)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

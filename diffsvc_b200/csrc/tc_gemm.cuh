@@ -189,6 +189,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
+// K-major operand tile whose rows are KB fp16 wide (KB = 64 / 32 / 16 -> SWIZZLE_128B / 64B / 32B, the narrow rows of the
+// vocoder's 32- and 16-channel stages): 8-row groups are 8 * row bytes apart
+template <int KB>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
+  static_assert(KB == 64 || KB == 32 || KB == 16, "operand rows of 128, 64 or 32 bytes");
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * KB * 2) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(KB == 64 ? 2 : (KB == 32 ? 4 : 6)) << 61;      // SWIZZLE_128B / 64B / 32B
+  return d;
+}
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -616,28 +629,32 @@ static inline int tc_encode_fn(PFN_encodeTiled* out) {
 }
 
 // activation plane [B][T][K] fp16, box = {64 channels, 128 frames, 1 item}
-static inline int tc_make_a_map(CUtensorMap* m, const __half* base, int B, int T, int K, int box_rows = TC_BM) {
+static inline CUtensorMapSwizzle tc_swizzle_of(int kb) {
+  return kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// (kb: fp16 elements per operand row -- 64, or 32 / 16 for the narrow vocoder stages whose K per tap is that small)
+static inline int tc_make_a_map(CUtensorMap* m, const __half* base, int B, int T, int K, int box_rows = TC_BM, int kb = TC_BK) {
   PFN_encodeTiled enc;
   DSVC_TRY(tc_encode_fn(&enc));
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)T * K * 2};
-  cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tc_swizzle_of(kb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A [%d][%d][%d]) failed: %d", B, T, K, (int)r); return DSVC_ECUDA; }
   return DSVC_OK;
 }
 // weight matrix [rows][K] fp16, box = {64, box_rows}
-static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows) {
+static inline int tc_make_b_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows, int kb = TC_BK) {
   PFN_encodeTiled enc;
   DSVC_TRY(tc_encode_fn(&enc));
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tc_swizzle_of(kb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B [%d][%d]) failed: %d", rows, K, (int)r); return DSVC_ECUDA; }
   return DSVC_OK;
 }

@@ -120,3 +120,35 @@ def test_ragged_tile_table_follows_the_lengths(monkeypatch, pack):
                 ref = O.sample(sd, sched, cond[b:b + 1, :, :n], x0[b:b + 1, :, :, :n], steps, noise[:, b:b + 1, :, :, :n])
             err = (xf[b:b + 1, :, :, :n] - ref).abs().max().item()
             assert err <= 1e-4, (lens, b, err)
+
+
+def test_vocoder_narrow_stages_on_tensor_cores(monkeypatch):
+    """The 32- / 16-channel ResBlock stages on the pair kernel's narrow-row instantiations (64- / 32-byte operand rows,
+    SWIZZLE_64B / 32B, one tap per pipeline stage, output channels in a zero-padded 64-wide tile): forced on
+    (DSVC_NSF_NARROW=1), forced off (=0: FFMA) and the size rule's own choice, all against the CPU oracle."""
+    from diffsvc_b200.vocoders.nsf_hifigan import NsfHifiGAN
+    from diffsvc_b200.hparams import hparams, DEFAULTS_44K
+    hparams.clear(); hparams.update(DEFAULTS_44K)
+    monkeypatch.delenv("DSVC_TC_BN", raising=False)
+    monkeypatch.setenv("DSVC_TC_PAIR", "1")
+    sd = O.synth_nsf_weights(O.NSF_H_44K)
+    B, T = 2, 41
+    g = torch.Generator().manual_seed(5)
+    mel = torch.randn(B, T, 128, generator=g) * 0.8 - 2.0
+    f0 = O.synth_f0(B, T)
+    rand_ini = torch.rand(B, 9, generator=g)
+    noise = torch.randn(B, T * 512, 9, generator=g)
+    with torch.no_grad():
+        ref = O.spec2wav(sd, O.NSF_H_44K, mel, f0, rand_ini, noise)
+    outs = {}
+    for narrow in ("1", "0", None):
+        if narrow is None:
+            monkeypatch.delenv("DSVC_NSF_NARROW", raising=False)
+        else:
+            monkeypatch.setenv("DSVC_NSF_NARROW", narrow)
+        voc = NsfHifiGAN.from_state_dict(dict(O.NSF_H_44K), sd, device=DEV)
+        outs[narrow] = voc.spec2wav_torch(mel.to(DEV), f0=f0.to(DEV), rand_ini=rand_ini, sine_noise=noise).cpu()
+        d = outs[narrow] - ref
+        assert d.pow(2).mean().sqrt().item() <= 1e-4 and d.abs().max().item() <= 5e-4, narrow
+    assert not torch.equal(outs["1"], outs["0"])          # the narrow-row kernels did run
+    assert torch.equal(outs[None], outs["1"])             # 2 x 41 frames: the size rule picks them
