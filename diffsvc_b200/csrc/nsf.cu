@@ -9,6 +9,7 @@
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
 #include "tc_pair.cuh"
+#include "tc_narrow.cuh"
 
 #include <memory>
 
@@ -252,7 +253,7 @@ struct ConvW {
   int Cin = 0, Cout = 0, K = 0;
   // tcgen05 path (ResBlock convs whose channel count tiles by 64): fp16 hi/lo weights [K][Cout][Cin] + their TMA maps
   bool tc = false;
-  int kb = 0;                 // narrow convs (Cin = 32 / 16) on tcgen05: operand rows of Cin fp16, weight rows zero-padded to 64 per tap
+  int kb = 0;                 // narrow convs (Cin = Cout = 32 / 16) on tcgen05 (tc_narrow.cuh): operand rows of Cin fp16
   F16Pair h16;
   CUtensorMap bh, bl, b32h, b32l, b64h, b64l;   // weight boxes of 128 / 32 / 64 rows (tc_gemm.cuh, tc_pair.cuh)
 };
@@ -305,18 +306,14 @@ static int upload_conv(ConvW& c, const float* w, const float* b, int Cout, int C
   DSVC_TRY(c.b.upload(b, (size_t)Cout * 4, s));
   c.tc = tc;
   if (tc && Cin < 64) {
-    // narrow conv: a tap is one pipeline stage of Cin / 16 MMA K-steps (64- / 32-byte operand rows, SWIZZLE_64B / 32B);
-    // the Cout < 64 output channels ride in the 64-wide tile: [tap][64 rows, zero beyond Cout][Cin]
-    std::vector<float> r2((size_t)K * 64 * Cin, 0.f);
-    for (int k = 0; k < K; ++k)
-      for (int co = 0; co < Cout; ++co)
-        memcpy(&r2[((size_t)k * 64 + co) * Cin], &r[((size_t)k * Cout + co) * Cin], (size_t)Cin * 4);
+    // narrow conv (tc_narrow.cuh): the whole [tap][Cout][Cin] set sits in shared memory, one box of Cout rows per tap
+    DSVC_REQUIRE(Cin == Cout && (Cin == 32 || Cin == 16), "narrow tcgen05 conv needs Cin == Cout in {32, 16} (got %d -> %d)", Cin, Cout);
     c.kb = Cin;
-    DSVC_TRY(c.w.upload(r.data(), r.size() * 4, s));     // the FFMA form too: long clips keep the narrow stages there (nsf_narrow_tc)
-    DSVC_TRY(make_f16_pair(c.h16, r2.data(), r2.size(), s));
-    DSVC_TRY(tc_make_b_map(&c.b32h, c.h16.hi.as<__half>(), K * 64, Cin, 32, Cin));
-    DSVC_TRY(tc_make_b_map(&c.b32l, c.h16.lo.as<__half>(), K * 64, Cin, 32, Cin));
-    c.bh = c.b64h = c.b32h; c.bl = c.b64l = c.b32l;      // (only the 64-wide pair tile exists for narrow rows)
+    DSVC_TRY(c.w.upload(r.data(), r.size() * 4, s));     // the FFMA form too (DSVC_NSF_NARROW=0, pairs off)
+    DSVC_TRY(make_f16_pair(c.h16, r.data(), r.size(), s));
+    DSVC_TRY(tc_make_b_map(&c.b32h, c.h16.hi.as<__half>(), K * Cout, Cin, Cout, Cin));
+    DSVC_TRY(tc_make_b_map(&c.b32l, c.h16.lo.as<__half>(), K * Cout, Cin, Cout, Cin));
+    c.bh = c.b64h = c.b32h; c.bl = c.b64l = c.b32l;
   } else if (tc) {   // the tcgen05 path reads only the fp16 pair (same [tap][Cout][Cin] row order)
     DSVC_TRY(make_f16_pair(c.h16, r.data(), r.size(), s));
     DSVC_TRY(tc_make_b_map(&c.bh, c.h16.hi.as<__half>(), K * Cout, Cin, 128));
@@ -384,27 +381,17 @@ static int conv_same_tc(const ConvW& c, const TcGemmMaps& in, EpiVoc::Params e, 
   TcGemmMaps g = in;
   g.b_hi = c.bh; g.b_lo = c.bl; g.b32_hi = c.b32h; g.b32_lo = c.b32l; g.b64_hi = c.b64h; g.b64_lo = c.b64l;
   e.bias = c.b.as<float>(); e.Lout = L; e.Cout = c.Cout; e.wscale = c.h16.inv_scale;
-  if (c.kb == 32) return tc_pair_launch_bn<EpiVoc, 64, 32>(g, e, B, L, c.Cin, 64, c.K, dil, s);
-  if (c.kb == 16) return tc_pair_launch_bn<EpiVoc, 64, 16>(g, e, B, L, c.Cin, 64, c.K, dil, s);
+  if (c.kb == 32) return tc_narrow_launch<32>(in.a_hi, in.a_lo, c.b32h, c.b32l, e, B, L, c.K, dil, s);
+  if (c.kb == 16) return tc_narrow_launch<16>(in.a_hi, in.a_lo, c.b32h, c.b32l, e, B, L, c.K, dil, s);
   return tc_launch<EpiVoc>(g, e, B, L, c.Cin, c.Cout, c.K, dil, 3, s);
 }
 
-// The 32- / 16-channel stages can run on the CTA-pair kernel's narrow-row instantiations (weights are kept in both forms).
+// The 32- / 16-channel stages run on the weights-stationary narrow kernel (tc_narrow.cuh); DSVC_NSF_NARROW=0 keeps them
+// on the FFMA GEMM (their weights are kept in both forms).
 static bool nsf_tc_channels(int ch) {
   if (ch % 64 == 0) return true;
   const char* e = getenv("DSVC_NSF_NARROW");
-  return (ch == 32 || ch == 16) && tc_pair_enabled() && !(e && atoi(e) == 0);
-}
-// ... and do when the stage is short.  One tap per pipeline stage moves 20 KB of operands for 192 MMA cycles and every
-// 256-row pair tile pays a CTA launch, so per frame the narrow tcgen05 kernels cost MORE than the FFMA GEMM (measured, one
-// 862-frame clip: 7.51 vs 6.62 ms per vocoder pass), but their latency is lower (43 frames: 1.31 vs 1.66 ms): crossover at
-// ~275 mel frames (profiles/r2e_vocoder_narrow.txt).  Rule: tensor cores while the 32-channel stage's frame tiles fit
-// four waves of the SMs.  DSVC_NSF_NARROW=1 forces them on, =0 off.
-static bool nsf_narrow_tc(int B, int len, int ch) {
-  const char* e = getenv("DSVC_NSF_NARROW");
-  if (e && atoi(e) >= 1) return true;
-  const long long tiles32 = (long long)B * ceil_div(ch == 32 ? len : len / 2, TC_BM);
-  return tiles32 <= 4 * 148;
+  return (ch == 32 || ch == 16) && !(e && atoi(e) == 0);
 }
 
 // (re)build the activation-plane maps for a (B, T) shape
@@ -417,12 +404,13 @@ static int nsf_build_maps(dsvc_nsf* h, int B, int T) {
     len *= cfg.upsample_rates[i];
     ch >>= 1;
     NsfStageMaps& m = h->smaps[i];
-    m.tc = h->tc_enabled && nsf_tc_channels(ch) && (ch >= 64 || nsf_narrow_tc(B, len, ch));
+    m.tc = h->tc_enabled && nsf_tc_channels(ch);
     if (!m.tc) continue;
-    const int kb = ch < 64 ? ch : TC_BK;      // operand row width: the narrow stages' K per tap is the channel count
+    // narrow stages: operand rows of `ch` fp16 and one 192-row window per tile (tc_narrow.cuh); else [128 x 64] tiles
+    const int kb = ch < 64 ? ch : TC_BK, box_rows = ch < 64 ? NW_WIN : TC_BM;
     auto planes = [&](TcGemmMaps& g, const PlaneBuf& pb) -> int {
-      DSVC_TRY(tc_make_a_map(&g.a_hi, pb.hi.as<__half>(), B, len, ch, TC_BM, kb));
-      DSVC_TRY(tc_make_a_map(&g.a_lo, pb.lo.as<__half>(), B, len, ch, TC_BM, kb));
+      DSVC_TRY(tc_make_a_map(&g.a_hi, pb.hi.as<__half>(), B, len, ch, box_rows, kb));
+      DSVC_TRY(tc_make_a_map(&g.a_lo, pb.lo.as<__half>(), B, len, ch, box_rows, kb));
       return DSVC_OK;
     };
     DSVC_TRY(planes(m.px, h->PX));

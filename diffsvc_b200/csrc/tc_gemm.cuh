@@ -238,7 +238,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 template <int CW> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&r)[CW]);
+template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, float (&r)[8]) { tmem_ld8(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, float (&r)[4]) { tmem_ld4(taddr, r); }
 template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float (&r)[32]) { tmem_ld32(taddr, r); }
 template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&r)[16]) { tmem_ld16(taddr, r); }
 

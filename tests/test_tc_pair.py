@@ -123,9 +123,9 @@ def test_ragged_tile_table_follows_the_lengths(monkeypatch, pack):
 
 
 def test_vocoder_narrow_stages_on_tensor_cores(monkeypatch):
-    """The 32- / 16-channel ResBlock stages on the pair kernel's narrow-row instantiations (64- / 32-byte operand rows,
-    SWIZZLE_64B / 32B, one tap per pipeline stage, output channels in a zero-padded 64-wide tile): forced on
-    (DSVC_NSF_NARROW=1), forced off (=0: FFMA) and the size rule's own choice, all against the CPU oracle."""
+    """The 32- / 16-channel ResBlock stages on the weights-stationary narrow kernel (csrc/tc_narrow.cuh: 64- / 32-byte
+    operand rows, SWIZZLE_64B / 32B, every tap fed from one 192-row activation window at a row offset): on
+    (DSVC_NSF_NARROW=1), off (=0: FFMA GEMM) and the default (on), all against the CPU oracle."""
     from diffsvc_b200.vocoders.nsf_hifigan import NsfHifiGAN
     from diffsvc_b200.hparams import hparams, DEFAULTS_44K
     hparams.clear(); hparams.update(DEFAULTS_44K)
@@ -151,4 +151,4 @@ def test_vocoder_narrow_stages_on_tensor_cores(monkeypatch):
         d = outs[narrow] - ref
         assert d.pow(2).mean().sqrt().item() <= 1e-4 and d.abs().max().item() <= 5e-4, narrow
     assert not torch.equal(outs["1"], outs["0"])          # the narrow-row kernels did run
-    assert torch.equal(outs[None], outs["1"])             # 2 x 41 frames: the size rule picks them
+    assert torch.equal(outs[None], outs["1"])             # the default
