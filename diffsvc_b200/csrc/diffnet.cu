@@ -185,6 +185,9 @@ struct dsvc_diffnet {
   int num_sms = 148;
   // CUDA graphs of one sampler step
   cudaGraphExec_t g_ddpm = nullptr, g_plms = nullptr;
+  cudaGraphExec_t g_ddpm_x = nullptr;  // DDPM_UNROLL consecutive steps in one graph: the programmatic (PDL) edges then run on
+                                       // across the step boundary, which a graph launch boundary serialises
+  uint64_t g_ddpm_x_nodes = 0;
   cudaStream_t cap_stream = nullptr;   // private stream used only to record graphs (the caller's may be the
                                        // legacy default stream, which cannot be captured)
   uint64_t g_ddpm_nodes = 0, g_plms_nodes = 0;   // kernels per replay of each graph
@@ -192,6 +195,7 @@ struct dsvc_diffnet {
 
   ~dsvc_diffnet() {
     if (g_ddpm) cudaGraphExecDestroy(g_ddpm);
+    if (g_ddpm_x) cudaGraphExecDestroy(g_ddpm_x);
     if (g_plms) cudaGraphExecDestroy(g_plms);
     if (cap_stream) cudaStreamDestroy(cap_stream);
   }
@@ -897,10 +901,24 @@ int dsvc_sample_ddpm(dsvc_diffnet_t* h, float* x, int32_t t_start, const float* 
         DSVC_LAUNCH_CHECK();
         return DSVC_OK;
       }));
+      constexpr int DDPM_UNROLL = 10;
+      DSVC_TRY(capture_graph(h, &h->g_ddpm_x, &h->g_ddpm_x_nodes, [&](cudaStream_t cs) -> int {
+        for (int u = 0; u < DDPM_UNROLL; ++u) {
+          DSVC_TRY(enqueue_eval(h, ha, cs));
+          advance_state_kernel<<<1, 1, 0, cs>>>(h->state.as<StepState>(), 0);
+          DSVC_LAUNCH_CHECK();
+        }
+        return DSVC_OK;
+      }));
       h->g_ddpm_valid = true;
     }
-    for (int i = 0; i < t_start; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm, s));
-    g_launches.fetch_add(h->g_ddpm_nodes * (uint64_t)t_start, std::memory_order_relaxed);
+    {
+      constexpr int DDPM_UNROLL = 10;
+      const int blocks = t_start / DDPM_UNROLL, rest = t_start - blocks * DDPM_UNROLL;
+      for (int i = 0; i < blocks; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm_x, s));
+      for (int i = 0; i < rest; ++i) DSVC_CUDA(cudaGraphLaunch(h->g_ddpm, s));
+      g_launches.fetch_add(h->g_ddpm_x_nodes * (uint64_t)blocks + h->g_ddpm_nodes * (uint64_t)rest, std::memory_order_relaxed);
+    }
   }
   return store_x(h, x, s);
 }

@@ -35,18 +35,12 @@
 
 namespace dsvc {
 
-// KB: fp16 elements per operand row = K per pipeline stage.  64 (128-byte rows, SWIZZLE_128B) everywhere except the
-// vocoder's 32- and 16-channel ResBlock stages, whose K per tap is 32 / 16: their rows are 64 / 32 bytes (SWIZZLE_64B /
-// 32B), a tap is one stage of KB / 16 MMA K-steps, and the 32 / 16 output channels ride in a zero-padded 64-wide tile.
-template <int BN, int KB = TC_BK> struct TcPairCfg {
+template <int BN> struct TcPairCfg {
   static constexpr int H = BN / 2;
-  static constexpr int A_TILE = TC_BM * KB * 2;              // 128 rows x KB fp16
-  static constexpr int P_TILE = BN * KB * 2;                 // BN rows x KB fp16
-  static constexpr int STAGE = 2 * A_TILE + P_TILE;          // A_hi, A_lo, P
-  static constexpr int STAGES = KB < 64 ? 8 : ((BN == 64) ? 5 : (BN == 128 ? 4 : 3));   // 200 / 192 / 192 KB (KB = 64) in flight
+  static constexpr int P_TILE = BN * TC_BK * 2;              // BN rows x 128 B
+  static constexpr int STAGE = 2 * TC_A_TILE + P_TILE;       // A_hi, A_lo, P
+  static constexpr int STAGES = (BN == 64) ? 5 : (BN == 128 ? 4 : 3);   // 200 / 192 / 192 KB of operands in flight
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(KB == 64 || BN == 64, "narrow operand rows: 64-wide tiles only");
-  static_assert((2 * STAGES + 2) * 8 <= 256, "barrier block");
   static_assert(4 * 32 * (BN + 4) * 4 <= STAGES * STAGE, "epilogue staging must fit in the operand ring");
 };
 
@@ -79,16 +73,15 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <class Epi, int BN, int KB = TC_BK>
+template <class Epi, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const typename Epi::Params ep, int T, int K, int N, int taps, int dil, const int2* __restrict__ tiles) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-  using Cfg = TcPairCfg<BN, KB>;
+  using Cfg = TcPairCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int H = Cfg::H;
-  constexpr uint32_t ROWB = KB * 2;                // bytes per operand row
   pdl_launch_dependents();
   int m0 = blockIdx.x * TC_BM, b = blockIdx.z;
   if (tiles != nullptr) {
@@ -107,8 +100,8 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-  auto tile_a = [&](int s, int lo) { return smem_base + (uint32_t)s * Cfg::STAGE + (uint32_t)lo * Cfg::A_TILE; };
-  auto tile_p = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE + 2u * Cfg::A_TILE; };
+  auto tile_a = [&](int s, int lo) { return smem_base + (uint32_t)s * Cfg::STAGE + (uint32_t)lo * TC_A_TILE; };
+  auto tile_p = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE + 2u * TC_A_TILE; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef DSVC_TIMELINE
@@ -116,7 +109,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   TL_ENTRY();
 #endif
   const uint32_t rank = cluster_ctarank();       // 0 = even CTA (issues the MMAs), 1 = odd
-  const int kblocks = K / KB;
+  const int kblocks = K / TC_BK;
   const int total = taps * kblocks;
 
   if (warp == 0 && lane == 0) {
@@ -182,16 +175,16 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const uint32_t bar = full_bar_leader(s);
     const uint32_t p = tile_p(s);
     // even: [wh_a ; wl_b]    odd: [wh_b ; wl_a]
-    tma2_load_2d(&tmBh, bar, p, kb * KB, rank == 0 ? ra : rb);
-    tma2_load_2d(&tmBl, bar, p + (uint32_t)H * ROWB, kb * KB, rank == 0 ? rb : ra);
+    tma2_load_2d(&tmBh, bar, p, kb * TC_BK, rank == 0 ? ra : rb);
+    tma2_load_2d(&tmBl, bar, p + (uint32_t)H * 128u, kb * TC_BK, rank == 0 ? rb : ra);
     }
   };
   auto load_a = [&](int it, int s) {
     const int tap = it / kblocks, kb = it - tap * kblocks;
     const int frame = m0 + (tap - (taps >> 1)) * dil;
     const uint32_t bar = full_bar_leader(s);
-    tma2_load_3d(&tmAh, bar, tile_a(s, 0), kb * KB, frame, b);
-    tma2_load_3d(&tmAl, bar, tile_a(s, 1), kb * KB, frame, b);
+    tma2_load_3d(&tmAh, bar, tile_a(s, 0), kb * TC_BK, frame, b);
+    tma2_load_3d(&tmAl, bar, tile_a(s, 1), kb * TC_BK, frame, b);
   };
 
   if (warp == 0) {
@@ -232,15 +225,15 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       if (it == 0) TL_MARK(1);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint64_t ah = umma_desc_k<KB>(tile_a(s, 0)), al = umma_desc_k<KB>(tile_a(s, 1));
-        const uint64_t pd = umma_desc_k<KB>(tile_p(s));
+        const uint64_t ah = umma_desc_sw128(tile_a(s, 0)), al = umma_desc_sw128(tile_a(s, 1));
+        const uint64_t pd = umma_desc_sw128(tile_p(s));
 #pragma unroll
-        for (int k4 = 0; k4 < KB / 16; ++k4) {
+        for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
           const uint64_t koff = (uint64_t)((k4 * 32) >> 4);
           const uint32_t acc = (it > 0 || k4 > 0) ? 1u : 0u;
           if constexpr (BN == 256) {
             // three N = 256 MMAs, xh*wl in its own accumulator (columns 256..511), like the single-CTA 256-wide tile
-            const uint64_t pl = umma_desc_k<KB>(tile_p(s) + 128u * 128u);
+            const uint64_t pl = umma_desc_sw128(tile_p(s) + 128u * 128u);
             umma2_f16(tmem_base, ah + koff, pd + koff, idesc_lo, acc);
             umma2_f16(tmem_base + (uint32_t)BN, ah + koff, pl + koff, idesc_lo, acc);
             umma2_f16(tmem_base, al + koff, pd + koff, idesc_lo, 1u);
@@ -279,16 +272,15 @@ inline bool tc_pair_enabled() {
   return !(e && atoi(e) == 0);
 }
 
-template <class Epi, int BN, int KB = TC_BK>
+template <class Epi, int BN>
 int tc_pair_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil,
                       cudaStream_t s, TcTiles tt = TcTiles{}) {
-  DSVC_REQUIRE(K % KB == 0 && N % BN == 0, "tc_pair_launch: K=%d / N=%d do not tile by %d / %d", K, N, KB, BN);
-  DSVC_TRY((ensure_dyn_smem<tc_pair_kernel<Epi, BN, KB>>(TcPairCfg<BN, KB>::SMEM)));
+  DSVC_TRY((ensure_dyn_smem<tc_pair_kernel<Epi, BN>>(TcPairCfg<BN>::SMEM)));
   cudaLaunchConfig_t cfg{};
   // frame tiles in pairs (an odd last one pairs with an empty tile); a ragged batch's table has an even slot count
   cfg.gridDim = tt.tab ? dim3(tt.slots, N / BN, 1) : dim3(2 * ceil_div(ceil_div(T, TC_BM), 2), N / BN, B);
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcPairCfg<BN, KB>::SMEM;
+  cfg.dynamicSmemBytes = TcPairCfg<BN>::SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -301,7 +293,7 @@ int tc_pair_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B,
   cfg.numAttrs = 2;
   const CUtensorMap& bh = (BN == 64) ? m.b32_hi : m.b64_hi;      // boxes of H rows (BN = 256: two 64-row boxes per half)
   const CUtensorMap& bl = (BN == 64) ? m.b32_lo : m.b64_lo;
-  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<Epi, BN, KB>, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, tt.tab));
+  DSVC_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<Epi, BN>, m.a_hi, m.a_lo, bh, bl, e, T, K, N, taps, dil, tt.tab));
   DSVC_LAUNCH_CHECK();
   return DSVC_OK;
 }
@@ -310,10 +302,10 @@ int tc_pair_launch_bn(const TcGemmMaps& m, const typename Epi::Params& e, int B,
 // mode, the single-CTA kernel otherwise (1-pass "fast mode", the 256-wide tiles of large batches, odd widths).
 template <class Epi>
 int tc_launch(const TcGemmMaps& m, const typename Epi::Params& e, int B, int T, int K, int N, int taps, int dil, int passes,
-              cudaStream_t s, TcTiles tt = TcTiles{}, int bn_want = 0) {
+              cudaStream_t s, TcTiles tt = TcTiles{}) {
   DSVC_REQUIRE(K % TC_BK == 0, "tc_launch: K=%d must be a multiple of %d", K, TC_BK);
   if (passes == 3 && tc_pair_enabled()) {
-    const int bn = bn_want > 0 ? bn_want : tc_pick_bn(B, T, N, tt.live);
+    const int bn = tc_pick_bn(B, T, N, tt.live);
     if (bn == 64 && N % 64 == 0) return tc_pair_launch_bn<Epi, 64>(m, e, B, T, K, N, taps, dil, s, tt);
     if (bn == 128 && N % 128 == 0) return tc_pair_launch_bn<Epi, 128>(m, e, B, T, K, N, taps, dil, s, tt);
     if (bn == 256 && N % 256 == 0) return tc_pair_launch_bn<Epi, 256>(m, e, B, T, K, N, taps, dil, s, tt);
