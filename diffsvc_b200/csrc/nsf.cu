@@ -281,6 +281,7 @@ struct dsvc_nsf {
   dsvc_nsf_config cfg;
   int hop = 1;
   bool tc_enabled = true;      // DSVC_NSF_MATH=fp32 forces the FFMA path everywhere
+  bool narrow_ok = true;       // the 32- / 16-channel stages can take tc_narrow.cuh (window reach, DSVC_NSF_NARROW)
   PlaneBuf PX, PA, PT;         // leaky_relu'ed operand planes: stage input, ResBlock state, conv1 output
   std::vector<NsfStageMaps> smaps;
   int maps_B = 0, maps_T = 0;
@@ -388,10 +389,18 @@ static int conv_same_tc(const ConvW& c, const TcGemmMaps& in, EpiVoc::Params e, 
 
 // The 32- / 16-channel stages run on the weights-stationary narrow kernel (tc_narrow.cuh); DSVC_NSF_NARROW=0 keeps them
 // on the FFMA GEMM (their weights are kept in both forms).
-static bool nsf_tc_channels(int ch) {
+static bool nsf_tc_channels(const dsvc_nsf* h, int ch) {
   if (ch % 64 == 0) return true;
+  return (ch == 32 || ch == 16) && h->narrow_ok;
+}
+// ... when every ResBlock conv's taps stay inside the kernel's activation window (k/2 * dilation <= NW_PAD rows)
+static bool nsf_narrow_fits(const dsvc_nsf_config& cfg) {
   const char* e = getenv("DSVC_NSF_NARROW");
-  return (ch == 32 || ch == 16) && !(e && atoi(e) == 0);
+  if (e && atoi(e) == 0) return false;
+  for (int j = 0; j < cfg.num_kernels; ++j)
+    for (int m = 0; m < cfg.num_dilations; ++m)
+      if ((cfg.resblock_kernel_sizes[j] / 2) * std::max(1, cfg.resblock_dilation_sizes[j][m]) > NW_PAD) return false;
+  return true;
 }
 
 // (re)build the activation-plane maps for a (B, T) shape
@@ -404,7 +413,7 @@ static int nsf_build_maps(dsvc_nsf* h, int B, int T) {
     len *= cfg.upsample_rates[i];
     ch >>= 1;
     NsfStageMaps& m = h->smaps[i];
-    m.tc = h->tc_enabled && nsf_tc_channels(ch);
+    m.tc = h->tc_enabled && nsf_tc_channels(h, ch);
     if (!m.tc) continue;
     // narrow stages: operand rows of `ch` fp16 and one 192-row window per tile (tc_narrow.cuh); else [128 x 64] tiles
     const int kb = ch < 64 ? ch : TC_BK, box_rows = ch < 64 ? NW_WIN : TC_BM;
@@ -438,6 +447,7 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
   {
     const char* ev = getenv("DSVC_NSF_MATH");
     h->tc_enabled = !(ev && strcmp(ev, "fp32") == 0);
+    h->narrow_ok = nsf_narrow_fits(*cfg);
   }
   const int ns = cfg->num_upsamples, nk = cfg->num_kernels, nd = cfg->num_dilations, dim = cfg->harmonic_num + 1;
   int ch = cfg->upsample_initial_channel;
@@ -484,7 +494,7 @@ int dsvc_nsf_create(dsvc_nsf_t** out, const dsvc_nsf_config* cfg, const dsvc_nsf
         DSVC_REQUIRE(k % 2 == 1, "resblock kernel size %d must be odd", k);
         h->c1.emplace_back(new ConvW());
         h->c2.emplace_back(new ConvW());
-        const bool tc = h->tc_enabled && nsf_tc_channels(cout);
+        const bool tc = h->tc_enabled && nsf_tc_channels(h.get(), cout);
         DSVC_TRY(upload_conv(*h->c1[idx], w->convs1_w[idx], w->convs1_b[idx], cout, cout, k, s, tc));
         DSVC_TRY(upload_conv(*h->c2[idx], w->convs2_w[idx], w->convs2_b[idx], cout, cout, k, s, tc));
       }
@@ -530,7 +540,7 @@ int dsvc_nsf_forward(dsvc_nsf_t* h, const float* mel, const float* f0, const flo
     int ch = cfg.upsample_initial_channel;
     for (int i = 0; i < ns; ++i) {
       len *= cfg.upsample_rates[i]; ch >>= 1;
-      if (h->tc_enabled && nsf_tc_channels(ch)) tcact = std::max(tcact, len * ch * (size_t)B);
+      if (h->tc_enabled && nsf_tc_channels(h, ch)) tcact = std::max(tcact, len * ch * (size_t)B);
     }
     if (tcact) {
       DSVC_TRY(h->PX.reserve(tcact, true));
