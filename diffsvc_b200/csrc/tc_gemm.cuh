@@ -270,7 +270,9 @@ __device__ long long g_timeline[1024][16];
 #endif
 
 // ===== epilogue (all 16 warps): TMEM -> registers -> smem transpose -> fused functor -> global =====
-template <class Epi, int BN>
+// LEAN (the step kernel, whose epilogue warps have 96 registers): row inputs that were not loaded early come in batches of
+// 4 rows instead of all 8 -- one more round of load latency, 40 registers less.
+template <class Epi, int BN, bool LEAN = false>
 __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint8_t* smem_raw, uint32_t smem_base,
                                             uint32_t tmem_base, uint32_t tmem_full_bar, uint32_t tmem_parity, int T, int N,
                                             int m0, int ny, int b, int warp, int lane, bool two_acc
@@ -361,7 +363,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
         tmem_ld_cols<LW>(taddr, v);
         if (two_acc) {                           // 3-pass mode: add the xh*wl accumulator (columns BN..2BN)
           const uint32_t partner = pair_h == 0 ? (uint32_t)BN : (uint32_t)((cg * CW + c0) < pair_h ? 3 * pair_h : pair_h);
-          constexpr int PW = LW > 16 ? 16 : LW;  // in pieces of <= 16 columns: 48, not 64, accumulator registers live
+          constexpr int PW = (LEAN && LW > 16) ? 16 : LW;   // LEAN: in pieces of 16 columns (48, not 64, accumulator registers live)
 #pragma unroll
           for (int c1 = 0; c1 < LW; c1 += PW) {
             float v2[PW];
@@ -389,9 +391,7 @@ __device__ __forceinline__ void tc_epilogue(const typename Epi::Params& ep, uint
       const int ncol = col_of(h);
       const bool col_ok = Epi::kPair ? true : (ncol < N);
       const int ch = lc + h * LPR;
-      // row inputs in batches of <= 4 rows when they were not loaded early (wide tiles): 8 rows x (2 float4 + row id)
-      // would hold 80 registers across the whole functor loop
-      constexpr int RCH = kHoist ? NIT : (NIT > 4 ? 4 : NIT);
+      constexpr int RCH = (kHoist || !LEAN) ? NIT : (NIT > 4 ? 4 : NIT);
 #pragma unroll
       for (int i0 = 0; i0 < NIT; i0 += RCH) {
       EpiPre pre[RCH];

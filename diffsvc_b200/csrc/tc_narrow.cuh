@@ -3,9 +3,9 @@
 //
 //   D[frame][n] = sum_{tap} sum_{c < C} A[frame + (tap - taps/2) * dil][c] * W[tap][n][c]
 //
-// Why not the WaveNet main loop (tc_pair.cuh's narrow-row instantiation does run these convs, and is what short clips
-// used in between): there a tap is a pipeline stage -- 20 KB of operands through TMA and shared memory for 192 MMA
-// cycles -- and every 256-frame tile is a CTA launch; above ~275 mel frames that loses to the FFMA GEMM.  Here
+// Why not the WaveNet main loop (a narrow-row instantiation of tc_pair.cuh ran these convs in between):
+// there a tap is a pipeline stage -- 20 KB of operands through TMA and shared memory for 192 MMA cycles -- and every
+// 256-frame tile is a CTA launch; above ~275 mel frames that lost to the FFMA GEMM.  Here
 //   * the conv's whole weight set ([wh ; wl] per tap: taps x 4 KB at C = 32) is loaded into shared memory ONCE per CTA,
 //   * a tile's activations are loaded ONCE: a window of 192 rows (the 128 output frames +- 32: every tap of every
 //     ResBlock conv, k <= 11 x dilation <= 5, reaches at most 25 rows out), hi and lo planes, 24 KB -- and each tap's

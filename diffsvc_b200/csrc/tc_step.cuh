@@ -1,6 +1,6 @@
 // One launch per denoiser evaluation: the 2L+3 contractions of DiffNet as PHASES of one kernel of resident CTA pairs.
 //
-// Why: at one clip a WaveNet layer is two kernels whose boundary costs as much as their main loops --
+// Why it was built: at one clip a WaveNet layer is two kernels whose boundary costs as much as their main loops --
 // the dependent grid must drain, half of the next grid's CTAs cannot be pre-launched (96 + 96 CTAs > 148 SMs: they start
 // 1.5 us late and pay barrier init / TMEM alloc / cluster sync / cold tensor maps again), and the first operand tiles
 // travel L2 -> smem only then.  Here every CTA pair owns one (256-frame tile, channel tile) slot for the whole
@@ -20,8 +20,9 @@
 // The whole plan (tensor maps of every phase, epilogue parameter blocks, phase table: ~22 KB) is ONE __grid_constant__
 // kernel parameter, so the per-phase scalars stay in the constant bank exactly as in the per-layer kernels.
 //
-// Residency: all CTAs must be co-resident (a phase polls flags other CTAs raise).  The launcher checks
-// cudaOccupancyMaxActiveClusters >= pairs and falls back to the per-layer kernels otherwise (or with DSVC_STEP=0).
+// Residency: all CTAs must be co-resident (a phase polls flags other CTAs raise).  The launcher sizes the grid from
+// cudaOccupancyMaxActiveClusters (a pair then owns ceil(slots / pairs) slots) and a dependency wait that lasts ~4 s traps
+// instead of hanging the GPU.  Opt-in (DSVC_STEP=1): measured slower than the per-layer kernels, see DESIGN.md 3.1f.
 #pragma once
 #include "tc_pair.cuh"
 
@@ -295,19 +296,19 @@ tc_step_kernel(const __grid_constant__ StepPlan plan) {
         const uint32_t free_leader = mapa_cluster(acc_free_bar((int)buf), 0u);
         switch (P.kind) {
           case STEP_IN:
-            tc_epilogue<EpiInProj, BN>(plan.in, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
+            tc_epilogue<EpiInProj, BN, true>(plan.in, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
             break;
           case STEP_GATE:
-            tc_epilogue<EpiGate, BN>(plan.gate[P.epi], smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
+            tc_epilogue<EpiGate, BN, true>(plan.gate[P.epi], smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
             break;
           case STEP_OUT:
-            tc_epilogue<EpiOutProj, BN>(plan.out[P.epi], smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
+            tc_epilogue<EpiOutProj, BN, true>(plan.out[P.epi], smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
             break;
           case STEP_SKIP:
-            tc_epilogue<EpiSkipProj, BN>(plan.skip, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
+            tc_epilogue<EpiSkipProj, BN, true>(plan.skip, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
             break;
           default:
-            tc_epilogue<EpiHead, BN>(plan.head, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
+            tc_epilogue<EpiHead, BN, true>(plan.head, smem_raw, slab_base, acc_addr, full, par, T, P.N, m0, ny, 0, warp, lane, true STEP_TL_ARGS, H, free_leader);
             break;
         }
 #ifdef DSVC_TIMELINE
