@@ -52,9 +52,10 @@ class CondEncoder(nn.Module):
             T = m2p.shape[1]
             out = torch.empty(B, T, H, device=hub.device, dtype=torch.float32)
             f0d = torch.empty(B, T, device=hub.device, dtype=torch.float32)
-            _lib.check(_lib.load().dsvc_cond_encode(_lib.dptr(hub), _lib.dptr(m2p), _lib.dptr(f0c), _lib.dptr(emb), B, Th, T, H,
-                                                    int(hparams["f0_bin"]), float(hparams["f0_min"]), float(hparams["f0_max"]),
-                                                    _lib.dptr(out), _lib.dptr(f0d), _lib.current_stream()))
+            with torch.cuda.device(hub.device):
+                _lib.check(_lib.load().dsvc_cond_encode(_lib.dptr(hub), _lib.dptr(m2p), _lib.dptr(f0c), _lib.dptr(emb), B, Th, T, H,
+                                                        int(hparams["f0_bin"]), float(hparams["f0_min"]), float(hparams["f0_max"]),
+                                                        _lib.dptr(out), _lib.dptr(f0d), _lib.current_stream()))
             f0[mel2ph == 0] = 0                                # fs2.py:226-227 (in-place on the caller's tensor)
             pitch_pad = None
             ret["f0_denorm"] = f0d

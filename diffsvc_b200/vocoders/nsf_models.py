@@ -153,8 +153,9 @@ class Generator:
             sn = _lib.dptr(sine_noise)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        _lib.check(_lib.load().dsvc_nsf_forward(self._h, _lib.dptr(mel), None if f0 is None else _lib.dptr(f0), ri, sn, C.c_uint64(seed),
-                                                C.c_float(mel_scale), _lib.dptr(wav), B, T, _lib.current_stream()))
+        with torch.cuda.device(mel.device):      # the handle's kernels launch on the current device: the tensors' own
+            _lib.check(_lib.load().dsvc_nsf_forward(self._h, _lib.dptr(mel), None if f0 is None else _lib.dptr(f0), ri, sn, C.c_uint64(seed),
+                                                    C.c_float(mel_scale), _lib.dptr(wav), B, T, _lib.current_stream()))
         return wav
 
     def __call__(self, x, f0=None, **kw):
